@@ -1,0 +1,292 @@
+"""ORACLE (test infrastructure, not product code) -- linear solve and time loop.
+
+PARITY UNPINNED by the reference.  Restates the *structure* of
+  solve_linear_system / solve_newton_system     reference src/classes/NavierStokes.cpp:833-868, 541-567
+  PreconditionBlockTriangular::vmult            reference src/classes/NavierStokes.hpp:320-344
+  SolverGMRES defaults (left preconditioning, x0 = 0, stop on the preconditioned residual
+  against 1e-2*||b||_2, AdditionalData(150) -> Krylov dimension 148)   SURVEY.md A.6
+  run()                                         reference src/classes/NavierStokes.cpp:1044-1327
+
+The Trilinos preconditioner internals (Ifpack ILU, ML AMG) are third-party and absent;
+their applications are replaced here by exact sparse factorizations of the same blocks
+(`inner="exact"`), i.e. the ideal version of the same block-triangular operator.  Field
+parity of the CUDA path is checked against `direct_solve` (tight-tolerance mode).
+"""
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from . import assemble as asm
+from . import dofs as odofs
+from . import postprocess as pp
+
+
+def direct_solve(A, b):
+    return spla.splu(sp.csc_matrix(A)).solve(b)
+
+
+class NoConvergence(Exception):
+    def __init__(self, last_step, last_value):
+        super().__init__("GMRES did not converge")
+        self.last_step, self.last_value = last_step, last_value
+
+
+def gmres_left(A_mv, b, P_mv, tol_abs, max_it, n_tmp_vectors=150, x0=None):
+    """Restarted left-preconditioned GMRES, modified Gram-Schmidt, Givens rotations.
+    Iteration 0 checks ||P^-1 (b - A x0)||; Krylov dimension n_tmp_vectors - 2.
+    Returns (x, iterations, last_residual); raises NoConvergence like SolverControl."""
+    n = b.shape[0]
+    x = np.zeros(n) if x0 is None else x0.copy()
+    m = n_tmp_vectors - 2
+    it = 0
+    while True:
+        r = P_mv(b - A_mv(x)) if it > 0 or x0 is not None else P_mv(b.copy())
+        beta = np.linalg.norm(r)
+        if it == 0 and beta <= tol_abs:
+            return x, 0, beta
+        V = np.zeros((m + 1, n))
+        Hm = np.zeros((m + 1, m))
+        cs = np.zeros(m)
+        sn = np.zeros(m)
+        g = np.zeros(m + 1)
+        g[0] = beta
+        V[0] = r / beta
+        k_used = 0
+        res = beta
+        converged = False
+        for k in range(m):
+            w = P_mv(A_mv(V[k]))
+            for i in range(k + 1):
+                Hm[i, k] = np.dot(w, V[i])
+                w -= Hm[i, k] * V[i]
+            Hm[k + 1, k] = np.linalg.norm(w)
+            if Hm[k + 1, k] > 0:
+                V[k + 1] = w / Hm[k + 1, k]
+            for i in range(k):
+                t = cs[i] * Hm[i, k] + sn[i] * Hm[i + 1, k]
+                Hm[i + 1, k] = -sn[i] * Hm[i, k] + cs[i] * Hm[i + 1, k]
+                Hm[i, k] = t
+            d = np.hypot(Hm[k, k], Hm[k + 1, k])
+            cs[k], sn[k] = Hm[k, k] / d, Hm[k + 1, k] / d
+            Hm[k, k] = d
+            Hm[k + 1, k] = 0.0
+            g[k + 1] = -sn[k] * g[k]
+            g[k] = cs[k] * g[k]
+            res = abs(g[k + 1])
+            it += 1
+            k_used = k + 1
+            if res <= tol_abs:
+                converged = True
+                break
+            if it >= max_it:
+                break
+        y = np.linalg.solve(np.triu(Hm[:k_used, :k_used]), g[:k_used])
+        x = x + V[:k_used].T @ y
+        if converged:
+            return x, it, res
+        if it >= max_it:
+            err = NoConvergence(it, res)
+            err.x = x
+            raise err
+
+
+class BlockTriangular:
+    """y0 = F~^-1 x0 ; t = x1 - B y0 ; y1 = -(rho/dt) Kp~^-1 t - theta*nu Mp~^-1 t   (hpp:320-344)."""
+
+    def __init__(self, A, Mp, Kp, n_u, nu, rho, dt, theta, inner="exact", cheb=None):
+        self.n_u = n_u
+        self.B = sp.csr_matrix(A[n_u:, :n_u])
+        self.nu, self.rho, self.dt, self.theta = nu, rho, dt, theta
+        F = sp.csc_matrix(A[:n_u, :n_u])
+        Mp11 = sp.csc_matrix(Mp[n_u:, n_u:])
+        Kp11 = sp.csc_matrix(Kp[n_u:, n_u:])
+        if inner == "exact":
+            self.Finv = spla.splu(F).solve
+            self.Mpinv = spla.splu(Mp11).solve
+            self.Kpinv = spla.splu(Kp11).solve
+        else:
+            raise ValueError(inner)
+
+    def __call__(self, x):
+        n_u = self.n_u
+        y0 = self.Finv(x[:n_u])
+        t = x[n_u:] - self.B @ y0
+        y1 = -(self.rho / self.dt) * self.Kpinv(t) - (self.theta * self.nu) * self.Mpinv(t)
+        return np.concatenate([y0, y1])
+
+
+class Oracle:
+    """Host-side mirror of NavierStokes<dim> for one rank, enough to step the reference's
+    run() loop (cpp:1044-1327) with either the reference stopping rule (GMRES, 1e-2) or a
+    direct solve (parity mode)."""
+
+    def __init__(self, mesh, case, solver="direct", deltat=None):
+        tc = dict(pp.TEST_CASES[case]) if isinstance(case, str) else dict(case)
+        self.tc = tc
+        self.mesh = mesh
+        self.dim = mesh.dim
+        assert self.dim == tc["dim"]
+        self.dm = odofs.enumerate_dofs(mesh)
+        self.pattern = odofs.make_sparsity(self.dm)
+        self.ids = pp.boundary_ids(self.dim)
+        self.nu = pp.viscosity(self.dim, tc["U_m"], tc["Re"])
+        self.rho = 1.0
+        dt = tc["deltat"] if deltat is None else deltat
+        self.deltat = dt if dt > 0 else pp.default_deltat(tc["Re"])
+        self.theta = 0.5 if tc["scheme"] == "CN" else 1.0
+        self.time = 0.0
+        self.first_step, self.second_step = True, True
+        N = self.dm.n_dofs
+        self.solution_old = np.zeros(N)
+        self.solution_old_old = np.zeros(N)
+        self.current_solution = np.zeros(N)
+        self.solver = solver
+        self.Mp = self.Kp = None
+        self.newton_constraints = odofs.build_constraints(mesh, self.dm, None, self.ids, homogeneous=True)
+        self.gmres_iters = []
+
+    # -- pieces -------------------------------------------------------------------
+    def inlet(self, t):
+        tc = self.tc
+        return pp.inlet_profile(self.dim, tc["U_m"], tc["time_dep"], tc["T_ramp"], t)
+
+    def params(self, dt=None, theta=None, first_step=None):
+        return asm.Params(dt=self.deltat if dt is None else dt,
+                          theta=self.theta if theta is None else theta, nu=self.nu, rho=self.rho,
+                          use_supg=self.tc["supg"],
+                          first_step=self.first_step if first_step is None else first_step,
+                          second_step=self.second_step, backward_euler=(self.tc["scheme"] == "BE"))
+
+    def assemble_linearized(self, p):
+        con = odofs.build_constraints(self.mesh, self.dm, self.inlet(self.time), self.ids)
+        out = asm.assemble(self.mesh, self.dm, self.pattern, p, con, "linearized",
+                           self.solution_old, self.solution_old_old,
+                           with_pressure_matrices=self.Mp is None)
+        if self.Mp is None:
+            self.Mp, self.Kp = out.Mp, out.Kp
+        return out, con
+
+    def assemble_newton(self, p):
+        out = asm.assemble(self.mesh, self.dm, self.pattern, p, self.newton_constraints, "newton",
+                           self.current_solution, self.solution_old,
+                           with_pressure_matrices=self.Mp is None)
+        if self.Mp is None:
+            self.Mp, self.Kp = out.Mp, out.Kp
+        return out
+
+    def solve(self, out, con, p, max_it):
+        N = self.dm.n_dofs
+        A = asm.to_csr(self.pattern, out.A, N)
+        if self.solver == "direct":
+            x = direct_solve(A, out.b)
+            return con.distribute(x), True, 0
+        P = BlockTriangular(A, asm.to_csr(self.pattern, self.Mp, N), asm.to_csr(self.pattern, self.Kp, N),
+                            self.dm.n_u, p.nu, p.rho, p.dt, p.theta)
+        tol = 1e-2 * np.linalg.norm(out.b)
+        try:
+            x, it, _ = gmres_left(lambda v: A @ v, out.b, P, tol, max_it)
+            ok = True
+        except NoConvergence as e:
+            x, it, ok = e.x, e.last_step, False
+        self.gmres_iters.append(it)
+        return con.distribute(x), ok, it
+
+    # -- one time step of run() ---------------------------------------------------
+    def step(self):
+        tc = self.tc
+        self.time += self.deltat
+        theta_save = self.theta
+        if self.first_step and tc["scheme"] == "CN":
+            self.theta = 1.0
+        info = {}
+        if tc["method"] == "newton":
+            info = self._newton_step()
+        else:
+            info = self._linearized_step()
+        self.solution_old_old = self.solution_old.copy()
+        self.solution_old = self.current_solution.copy()
+        self.second_step = self.first_step
+        self.first_step = False
+        self.theta = theta_save
+        cd, cl = pp.lift_drag(self.mesh, self.dm, self.current_solution, self.nu, self.rho, tc["U_m"], self.ids["cylinder"])
+        dp = pp.pressure_difference(self.mesh, self.dm, self.current_solution)
+        info.update(time=self.time, cd=cd, cl=cl, dp=dp)
+        return info
+
+    def _linearized_step(self):
+        # cpp:1209-1289 (dt-halving retry with checkpoint, BE fallback, last resort)
+        chk_old, chk_oo, chk_first = self.solution_old.copy(), self.solution_old_old.copy(), self.first_step
+        dt_attempt = self.deltat
+        step_ok, substep = False, 0
+        x = None
+        its = []
+        while not step_ok and substep <= 4:
+            if substep > 0:
+                dt_attempt *= 0.5
+                self.solution_old, self.solution_old_old, self.first_step = chk_old.copy(), chk_oo.copy(), chk_first
+            p = self.params(dt=dt_attempt)
+            out, con = self.assemble_linearized(p)
+            x, ok, it = self.solve(out, con, p, 200)
+            its.append(it)
+            if not ok and substep == 0:
+                p = self.params(dt=dt_attempt, theta=1.0, first_step=True)
+                out, con = self.assemble_linearized(p)
+                x, ok, it = self.solve(out, con, p, 200)
+                its.append(it)
+            if ok:
+                step_ok = True
+            else:
+                substep += 1
+        if not step_ok:
+            self.solution_old, self.solution_old_old, self.first_step = chk_old.copy(), chk_oo.copy(), chk_first
+            p = self.params(dt=dt_attempt, theta=1.0, first_step=True)
+            out, con = self.assemble_linearized(p)
+            x, ok, it = self.solve(out, con, p, 200)
+            its.append(it)
+        self.current_solution = x
+        return dict(gmres=its, ok=step_ok)
+
+    def _newton_step(self):
+        # cpp:1116-1207
+        tc = self.tc
+        dm = self.dm
+        # lift non-homogeneous BCs onto current_solution (cpp:1118-1142)
+        fn = self.inlet(self.time)
+        d_in = odofs.boundary_dofs(self.mesh, dm, self.ids["inlet"])
+        bv = {}
+        for d, v in zip(d_in, fn(dm.support_points[d_in], dm.component[d_in])):
+            bv[int(d)] = v
+        for d in odofs.boundary_dofs(self.mesh, dm, self.ids["wall"]):
+            bv[int(d)] = 0.0                       # std::map overload: later calls overwrite
+        for d in odofs.boundary_dofs(self.mesh, dm, self.ids["cylinder"]):
+            bv[int(d)] = 0.0
+        for d, v in bv.items():
+            self.current_solution[d] = v
+        residual_norm, previous_residual = 1e10, 1e10
+        newton_iter, damping = 0, 1.0
+        res_hist, its = [], []
+        while residual_norm > 1e-8 and newton_iter < 50:
+            p = self.params()
+            out = self.assemble_newton(p)
+            residual_norm = np.linalg.norm(out.b)
+            res_hist.append(residual_norm)
+            if residual_norm < 1e-8:
+                break
+            if newton_iter > 0 and residual_norm > 0.99 * previous_residual:
+                damping = max(0.05, damping * 0.5)
+            elif residual_norm < 0.5 * previous_residual and damping < 1.0 - 1e-12:
+                damping = min(1.0, damping * 1.5)
+            previous_residual = residual_norm
+            backup = self.current_solution.copy()
+            upd, ok, it = self.solve(out, self.newton_constraints, p, 500)
+            its.append(it)
+            if not ok:
+                damping = max(0.05, damping * 0.25)
+            self.current_solution = self.current_solution + damping * upd
+            if not ok:
+                out2 = self.assemble_newton(p)
+                if np.linalg.norm(out2.b) > 2.0 * residual_norm:
+                    damping = max(0.01, damping * 0.5)
+                    self.current_solution = backup + damping * upd
+            newton_iter += 1
+        return dict(newton_iters=newton_iter, residuals=res_hist, gmres=its)
