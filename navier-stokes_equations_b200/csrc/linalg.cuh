@@ -1,0 +1,352 @@
+// Bandwidth-bound kernels of the Krylov solve: node-block SpMV (and its fused
+// Chebyshev / Schur variants), generic CSR kernels for the pressure multigrid, fused
+// multi-dot / multi-axpy for Gram-Schmidt, and small BLAS-1.
+//
+// Replaces the Epetra/Trilinos primitives behind
+//   SolverGMRES::solve(system_matrix, x, rhs, preconditioner)        reference NavierStokes.cpp:561, 853
+//   TrilinosWrappers::BlockSparseMatrix::vmult, B->vmult, sadd, add  reference NavierStokes.hpp:334-343
+// All reductions use fixed trees -> results are bit-reproducible run to run.
+#pragma once
+#include "device.cuh"
+
+namespace nsb {
+
+constexpr int SPMV_WARPS = 8;
+
+// ------------------------------------------------------------------------------------
+// y = A x over the node-block structure.  One warp per owned P2 node handles the node's
+// dim velocity rows (+ its pressure row when the node is a vertex): the rows share the
+// column set, so x is gathered once and every matrix value is streamed exactly once,
+// contiguously per row (coalesced 256-byte warp loads, evict-first).
+// ------------------------------------------------------------------------------------
+template <int DIM, typename VT>
+__global__ void __launch_bounds__(SPMV_WARPS * 32)
+k_spmv_full(DevMesh M, const VT* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int A = blockIdx.x * SPMV_WARPS + (threadIdx.x >> 5);
+  if (A >= M.nn_own) return;
+  const long long n0 = M.nbr_ptr[A], p0 = M.pnbr_ptr[A];
+  const int nb = (int)(M.nbr_ptr[A + 1] - n0), np = (int)(M.pnbr_ptr[A + 1] - p0);
+  const int nbd = DIM * nb, len = nbd + np;
+  const int pid = M.node_pid[A];
+  const bool isv = pid >= 0;
+  const VT* r0 = vals + M.rowbase[A];
+  const VT* rp = isv ? vals + M.prowbase[pid] : vals;
+  double sum[DIM + 1];
+#pragma unroll
+  for (int c = 0; c <= DIM; ++c) sum[c] = 0.0;
+  for (int k = lane; k < len; k += 32) {
+    const int xo = (k < nbd) ? (__ldg(M.nbr_xoff + n0 + k / DIM) + k % DIM) : __ldg(M.pnbr_xoff + p0 + (k - nbd));
+    const double xv = __ldg(x + xo);
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) sum[c] += (double)__ldcs(r0 + (long long)c * len + k) * xv;
+    if (isv) sum[DIM] += (double)__ldcs(rp + k) * xv;
+  }
+#pragma unroll
+  for (int c = 0; c <= DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
+  if (lane < DIM) {
+    double v = sum[0];
+#pragma unroll
+    for (int c = 1; c < DIM; ++c) if (lane == c) v = sum[c];
+    y[DIM * A + lane] = v;
+  }
+  if (isv && lane == DIM) y[DIM * M.nn_own + pid] = sum[DIM];
+}
+
+// ------------------------------------------------------------------------------------
+// Velocity block F = A(0,0) only (columns < dim*nb of the velocity rows), with the fused
+// epilogues of the block-Jacobi Chebyshev iteration used in place of Ifpack ILU(1)
+// (reference NavierStokes.hpp:302-304, 325):
+//   MODE 0:  y = F x
+//   MODE 1:  r = r0 - F z ; d = c1 d + c2 Dinv r ; znew = z + d            (one Chebyshev step)
+//   MODE 2:  y = Dinv (F x)                                               (power iteration)
+// ------------------------------------------------------------------------------------
+template <int DIM, int MODE, typename VT>
+__global__ void __launch_bounds__(SPMV_WARPS * 32)
+k_spmv_vel(DevMesh M, const VT* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+           const double* __restrict__ r0v, double* __restrict__ dv, const double* __restrict__ dinv,
+           double c1, double c2) {
+  const int lane = threadIdx.x & 31;
+  const int A = blockIdx.x * SPMV_WARPS + (threadIdx.x >> 5);
+  if (A >= M.nn_own) return;
+  const long long n0 = M.nbr_ptr[A];
+  const int nb = (int)(M.nbr_ptr[A + 1] - n0);
+  const int nbd = DIM * nb;
+  const int len = nbd + (int)(M.pnbr_ptr[A + 1] - M.pnbr_ptr[A]);
+  const VT* r0 = vals + M.rowbase[A];
+  double sum[DIM];
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) sum[c] = 0.0;
+  for (int k = lane; k < nbd; k += 32) {
+    const double xv = __ldg(x + __ldg(M.nbr_xoff + n0 + k / DIM) + k % DIM);
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) sum[c] += (double)__ldcs(r0 + (long long)c * len + k) * xv;
+  }
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
+  if (lane < DIM) {
+    const int row = DIM * A + lane;
+    if (MODE == 0) {
+      double v = sum[0];
+#pragma unroll
+      for (int c = 1; c < DIM; ++c) if (lane == c) v = sum[c];
+      y[row] = v;
+    } else {
+      double r[DIM];
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) r[c] = (MODE == 1) ? (r0v[DIM * A + c] - sum[c]) : sum[c];
+      double t = 0.0;
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) t += dinv[(size_t)A * DIM * DIM + lane * DIM + c] * r[c];
+      if (MODE == 1) {
+        const double dn = c1 * dv[row] + c2 * t;
+        dv[row] = dn;
+        y[row] = x[row] + dn;
+      } else {
+        y[row] = t;
+      }
+    }
+  }
+}
+
+// t = g - B y0 : pressure rows, velocity columns (reference NavierStokes.hpp:334-335)
+template <int DIM, typename VT>
+__global__ void __launch_bounds__(SPMV_WARPS * 32)
+k_schur_rhs(DevMesh M, const VT* __restrict__ vals, const double* __restrict__ y0, const double* __restrict__ g,
+            double* __restrict__ t) {
+  const int lane = threadIdx.x & 31;
+  const int Pid = blockIdx.x * SPMV_WARPS + (threadIdx.x >> 5);
+  if (Pid >= M.np_own) return;
+  const int A = M.pid_node[Pid];
+  const long long n0 = M.nbr_ptr[A];
+  const int nbd = DIM * (int)(M.nbr_ptr[A + 1] - n0);
+  const VT* rp = vals + M.prowbase[Pid];
+  double s = 0.0;
+  for (int k = lane; k < nbd; k += 32)
+    s += (double)__ldcs(rp + k) * __ldg(y0 + __ldg(M.nbr_xoff + n0 + k / DIM) + k % DIM);
+  s = warp_sum_fixed(s);
+  if (lane == 0) t[Pid] = g[DIM * M.nn_own + Pid] - s;
+}
+
+// dv = Dinv r / theta ; z = dv   (first Chebyshev step from z0 = 0), block version
+template <int DIM>
+__global__ void k_cheb_first_vel(int nn, const double* __restrict__ dinv, const double* __restrict__ r0,
+                                 double* __restrict__ dv, double* __restrict__ z, double inv_theta) {
+  const int A = blockIdx.x * blockDim.x + threadIdx.x;
+  if (A >= nn) return;
+  double r[DIM];
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) r[c] = r0[DIM * A + c];
+#pragma unroll
+  for (int e = 0; e < DIM; ++e) {
+    double t = 0.0;
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) t += dinv[(size_t)A * DIM * DIM + e * DIM + c] * r[c];
+    t *= inv_theta;
+    dv[DIM * A + e] = t;
+    z[DIM * A + e] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// generic CSR kernels (pressure mass matrix, pressure-Laplacian multigrid levels; these
+// matrices are L2-resident, the kernels are latency-bound)
+// ------------------------------------------------------------------------------------
+struct DevCsr {
+  int n = 0, m = 0;
+  const int* ptr = nullptr;
+  const int* col = nullptr;
+  const double* val = nullptr;
+};
+
+// MODE 0: y = A x ; 1: y = b - A x ; 2: y += A x ;
+// MODE 3: r = b - A x ; d = c1 d + c2 dinv r ; y = x + d     (scalar-Jacobi Chebyshev step)
+template <int MODE>
+__global__ void k_csr(DevCsr A, const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ b,
+                      double* __restrict__ d, const double* __restrict__ dinv, double c1, double c2) {
+  constexpr int LPR = 8;                            // lanes per row
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int sub = threadIdx.x % LPR;
+  double s = 0.0;
+  if (row < A.n)
+    for (int k = A.ptr[row] + sub; k < A.ptr[row + 1]; k += LPR) s += A.val[k] * __ldg(x + A.col[k]);
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(NSB_FULL, s, o);
+  if (row < A.n && sub == 0) {
+    if (MODE == 0) y[row] = s;
+    if (MODE == 1) y[row] = b[row] - s;
+    if (MODE == 2) y[row] += s;
+    if (MODE == 3) {
+      const double dn = c1 * d[row] + c2 * dinv[row] * (b[row] - s);
+      d[row] = dn;
+      y[row] = x[row] + dn;
+    }
+  }
+}
+
+__global__ void k_cheb_first(int n, const double* __restrict__ dinv, const double* __restrict__ b,
+                             double* __restrict__ d, double* __restrict__ x, double inv_theta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const double t = dinv[i] * b[i] * inv_theta; d[i] = t; x[i] = t; }
+}
+
+// y = Ainv b, dense n x n (coarsest multigrid level); one warp per row
+__global__ void k_dense_mv(int n, const double* __restrict__ Ainv, const double* __restrict__ b, double* __restrict__ y) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= n) return;
+  double s = 0.0;
+  for (int k = lane; k < n; k += 32) s += Ainv[(size_t)row * n + k] * b[k];
+  s = warp_sum_fixed(s);
+  if (lane == 0) y[row] = s;
+}
+
+// ------------------------------------------------------------------------------------
+// BLAS-1
+// ------------------------------------------------------------------------------------
+constexpr int RED_THREADS = 256;
+constexpr int RED_ELEMS = 8;                         // elements per thread per chunk
+constexpr int RED_CHUNK = RED_THREADS * RED_ELEMS;   // rows per block
+
+__device__ __forceinline__ double block_sum_fixed(double v, double* sbuf) {
+  v = warp_sum_fixed(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sbuf[wid] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (wid == 0) {
+    t = (lane < (int)(blockDim.x >> 5)) ? sbuf[lane] : 0.0;
+    t = warp_sum_fixed(t);
+  }
+  __syncthreads();
+  return t;     // valid on warp 0
+}
+
+// partial[j*nblk + blk] = sum over the block's chunk of V_j[i] * w[i],  j = 0..nv-1.
+// V_j = V + j*ld.  One pass over w, one pass over each V_j.
+__global__ void __launch_bounds__(RED_THREADS)
+k_multi_dot(int nv, const double* __restrict__ V, long long ld, const double* __restrict__ w, long long n,
+            double* __restrict__ partial) {
+  __shared__ double sbuf[RED_THREADS / 32];
+  const long long base = (long long)blockIdx.x * RED_CHUNK;
+  double wv[RED_ELEMS];
+#pragma unroll
+  for (int e = 0; e < RED_ELEMS; ++e) {
+    const long long i = base + e * RED_THREADS + threadIdx.x;
+    wv[e] = (i < n) ? w[i] : 0.0;
+  }
+  for (int j = 0; j < nv; ++j) {
+    const double* vj = V + (long long)j * ld;
+    double s = 0.0;
+#pragma unroll
+    for (int e = 0; e < RED_ELEMS; ++e) {
+      const long long i = base + e * RED_THREADS + threadIdx.x;
+      if (i < n) s += __ldcs(vj + i) * wv[e];
+    }
+    s = block_sum_fixed(s, sbuf);
+    if (threadIdx.x == 0) partial[(long long)j * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+// out[j] (+)= sum_blk partial[j*nblk + blk]   (one block per j, fixed order)
+__global__ void __launch_bounds__(RED_THREADS)
+k_reduce_partials(int nblk, const double* __restrict__ partial, double* __restrict__ out, int accumulate) {
+  __shared__ double sbuf[RED_THREADS / 32];
+  const int j = blockIdx.x;
+  double s = 0.0;
+  for (int k = threadIdx.x; k < nblk; k += RED_THREADS) s += partial[(long long)j * nblk + k];
+  s = block_sum_fixed(s, sbuf);
+  if (threadIdx.x == 0) out[j] = accumulate ? out[j] + s : s;
+}
+
+// w -= sum_j h[j] V_j  (sign = -1)   or   x += sum_j h[j] V_j  (sign = +1);
+// optionally also writes the per-block partial of ||w||^2 afterwards.
+__global__ void __launch_bounds__(RED_THREADS)
+k_multi_axpy(int nv, const double* __restrict__ V, long long ld, const double* __restrict__ h, double sign,
+             double* __restrict__ w, long long n, double* __restrict__ nrm_partial) {
+  __shared__ double sbuf[RED_THREADS / 32];
+  __shared__ double sh[160];
+  for (int j = threadIdx.x; j < nv; j += RED_THREADS) sh[j] = sign * h[j];
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * RED_CHUNK;
+  double acc[RED_ELEMS];
+#pragma unroll
+  for (int e = 0; e < RED_ELEMS; ++e) {
+    const long long i = base + e * RED_THREADS + threadIdx.x;
+    acc[e] = (i < n) ? w[i] : 0.0;
+  }
+  for (int j = 0; j < nv; ++j) {
+    const double* vj = V + (long long)j * ld;
+    const double hj = sh[j];
+#pragma unroll
+    for (int e = 0; e < RED_ELEMS; ++e) {
+      const long long i = base + e * RED_THREADS + threadIdx.x;
+      if (i < n) acc[e] += hj * __ldg(vj + i);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int e = 0; e < RED_ELEMS; ++e) {
+    const long long i = base + e * RED_THREADS + threadIdx.x;
+    if (i < n) { w[i] = acc[e]; s += acc[e] * acc[e]; }
+  }
+  if (nrm_partial) {
+    s = block_sum_fixed(s, sbuf);
+    if (threadIdx.x == 0) nrm_partial[blockIdx.x] = s;
+  }
+}
+
+// partial ||x||^2
+__global__ void __launch_bounds__(RED_THREADS)
+k_norm2_partial(const double* __restrict__ x, long long n, double* __restrict__ partial) {
+  __shared__ double sbuf[RED_THREADS / 32];
+  const long long base = (long long)blockIdx.x * RED_CHUNK;
+  double s = 0.0;
+#pragma unroll
+  for (int e = 0; e < RED_ELEMS; ++e) {
+    const long long i = base + e * RED_THREADS + threadIdx.x;
+    if (i < n) { const double v = x[i]; s += v * v; }
+  }
+  s = block_sum_fixed(s, sbuf);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// y = alpha[0-dim device scalar inverse-sqrt] * x : v_{k+1} = w / ||w||, norm2 read from device memory
+__global__ void k_scale_by_inv_norm(long long n, const double* __restrict__ x, const double* __restrict__ nrm2,
+                                    double* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const double s = 1.0 / sqrt(*nrm2);
+  if (i < n) y[i] = x[i] * s;
+}
+
+__global__ void k_axpby(long long n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a * x[i] + b * y[i];
+}
+
+// y = a*x + b*z
+__global__ void k_lincomb(long long n, double a, const double* __restrict__ x, double b, const double* __restrict__ z,
+                          double* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a * x[i] + b * z[i];
+}
+
+// scatter constraint values / flags;  x[dof] = val  (constraints.distribute, reference cpp:566, 862)
+__global__ void k_scatter_vals(int n, const int* __restrict__ idx, const double* __restrict__ val, double* __restrict__ x) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[idx[i]] = val[i];
+}
+__global__ void k_scatter_flags(int n, const int* __restrict__ idx, unsigned char* __restrict__ f, unsigned char v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) f[idx[i]] = v;
+}
+__global__ void k_gather(int n, const int* __restrict__ idx, const double* __restrict__ x, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = x[idx[i]];
+}
+// packs dim consecutive values per node index (halo send buffers)
+__global__ void k_gather_nodes(int n, int dim, const int* __restrict__ xoff, const double* __restrict__ x, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * dim) out[i] = x[xoff[i / dim] + i % dim];
+}
+
+}  // namespace nsb

@@ -1,0 +1,1194 @@
+// C-ABI implementation (include/nsb200.h): device context, uploads, the two assembly
+// passes, the block-triangular preconditioner and restarted GMRES.  sm_100a only; there is
+// no CPU fallback -- every entry point fails loudly when no CUDA device is usable.
+#include "../../include/nsb200.h"
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "amg.hpp"
+#include "assemble.cuh"
+#include "device.cuh"
+#include "linalg.cuh"
+#include "structure.hpp"
+
+using namespace nsb;
+
+namespace {
+
+struct CudaErr {
+  std::string msg;
+};
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      throw CudaErr{std::string(#call) + " failed: " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                    std::to_string(__LINE__) + ")"};                                               \
+  } while (0)
+#define CKN(call)                                                                        \
+  do {                                                                                   \
+    ncclResult_t r_ = (call);                                                            \
+    if (r_ != ncclSuccess)                                                               \
+      throw CudaErr{std::string(#call) + " failed: " + ncclGetErrorString(r_)};          \
+  } while (0)
+
+template <typename T> struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { if (p) cudaFree(p); }
+  void alloc(size_t count) {
+    if (p) { cudaFree(p); p = nullptr; }
+    n = count;
+    if (count) CK(cudaMalloc(&p, count * sizeof(T)));
+  }
+  void zero(cudaStream_t s) { if (n) CK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+  void upload(const std::vector<T>& v, cudaStream_t s) {
+    alloc(v.size());
+    if (n) CK(cudaMemcpyAsync(p, v.data(), n * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+};
+
+enum ProfCat { PC_ASM_CTX = 0, PC_ASM_ROWS, PC_SPMV, PC_SPMV_VEL, PC_SCHUR, PC_AMG, PC_ORTH, PC_OTHER, PC_N };
+const char* kProfNames[PC_N] = {"asm_context", "asm_rows", "spmv", "spmv_vel", "schur", "amg", "orth", "other"};
+
+struct Prof {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Rec { int cat; size_t e0, e1; };
+  std::vector<Rec> recs;
+  double ms[PC_N] = {0};
+  int64_t cnt[PC_N] = {0};
+  cudaEvent_t get() {
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[used++];
+  }
+  size_t begin(int cat, cudaStream_t s) {
+    if (!on) return 0;
+    Rec r{cat, used, 0};
+    cudaEventRecord(get(), s);
+    recs.push_back(r);
+    return recs.size() - 1;
+  }
+  void end(size_t id, cudaStream_t s) {
+    if (!on) return;
+    recs[id].e1 = used;
+    cudaEventRecord(get(), s);
+  }
+  void collect(cudaStream_t s) {
+    if (recs.empty()) return;
+    cudaStreamSynchronize(s);
+    for (auto& r : recs) {
+      float t = 0;
+      cudaEventElapsedTime(&t, pool[r.e0], pool[r.e1]);
+      ms[r.cat] += t;
+      cnt[r.cat]++;
+    }
+    recs.clear();
+    used = 0;
+  }
+  void reset() { for (int i = 0; i < PC_N; ++i) { ms[i] = 0; cnt[i] = 0; } recs.clear(); used = 0; }
+  ~Prof() { for (auto e : pool) cudaEventDestroy(e); }
+};
+
+struct DevLevel {
+  DevCsr A, P, R;
+  DBuf<int> Aptr, Acol, Pptr, Pcol, Rptr, Rcol;
+  DBuf<double> Aval, Pval, Rval, dinv;
+  DBuf<double> x, x2, b, d, r;
+  double lmax = 1.0;
+  int n = 0;
+};
+
+struct HaloBuf {
+  DBuf<double> u, p;
+  DBuf<int> uoff, poff;
+};
+
+void upload_csr(const HostCsr& H, DBuf<int>& ptr, DBuf<int>& col, DBuf<double>& val, DevCsr& D, cudaStream_t s) {
+  ptr.upload(H.ptr, s); col.upload(H.col, s); val.upload(H.val, s);
+  D.n = H.n; D.m = H.m; D.ptr = ptr.p; D.col = col.p; D.val = val.p;
+}
+
+}  // namespace
+
+struct nsb_ctx {
+  int dim = 0, device = 0;
+  int rank = 0, nranks = 1;
+  ncclComm_t comm = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  bool have_mesh = false, have_matrix = false, have_pressure = false;
+  int64_t launches = 0;
+  Prof prof;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+
+  // global mesh copies needed later on the host (pressure matrices)
+  int64_t n_vertices = 0, n_cells = 0, n_u = 0, n_p = 0;
+  std::vector<double> coords;
+  std::vector<uint32_t> cell_vertices;
+  std::vector<int> g_cell_pid;      // [C][NV] global pressure ids
+  Structure S;
+  DevMesh M{};
+  // device copies of the structure
+  DBuf<int> d_cell_xoff, d_cell_poff, d_nbr_xoff, d_pnbr_xoff, d_selfrank, d_node_pid, d_pid_node, d_pselfrank, d_tile_ptr;
+  DBuf<double> d_cell_geom;
+  DBuf<uint16_t> d_rank_uu, d_rank_up;
+  DBuf<long long> d_nbr_ptr, d_pnbr_ptr, d_rowbase, d_prowbase, d_n2c_ptr;
+  DBuf<uint32_t> d_n2c;
+  int n_tiles = 0, tile_smem_bytes = 0;
+  // global dof -> local vector offset (or -1)
+  std::vector<int> g2x;
+  DBuf<int> d_own_gather;           // unused on device; host maps instead
+  // vectors, all in local layout [u_own | p_own | u_ghost | p_ghost]
+  DBuf<double> v_old, v_oldold, v_cur, v_sol, v_rhs;
+  DBuf<unsigned char> cflag;
+  DBuf<double> cval;
+  DBuf<int> c_idx;                  // local offsets of the current constraint set
+  DBuf<double> c_val;
+  int n_con = 0;
+  // system
+  nsb_params par{};
+  nsb_solver_opts opt{};
+  DBuf<double> vals, dinv, ctx, cell_rhs;
+  int ctx_stride = 0;
+  // pressure matrices (global, replicated)
+  HostCsr h_Mp, h_Kp;
+  DevCsr Mp{};
+  DBuf<int> Mp_ptr, Mp_col;
+  DBuf<double> Mp_val, Mp_dinv;
+  double Mp_lmax = 1.0;
+  std::vector<std::unique_ptr<DevLevel>> amg;
+  std::vector<std::unique_ptr<HaloBuf>> halo;
+  DBuf<double> coarse_inv;
+  int coarse_n = 0;
+  // preconditioner / Krylov workspace
+  DBuf<double> w_z0, w_z1, w_d, w_t, w_y1, w_m0, w_m1, w_md, w_in, w_tmp, w_pin;
+  DBuf<double> V;                   // Krylov basis, (m+1) vectors of n_own
+  int V_cap = 0;
+  DBuf<double> partial, d_h, d_nrm;
+  double F_lmax = 0.0;
+  DBuf<double> eigv;                // power-iteration vector for lambda_max(Dinv F)
+  bool eig_init = false;
+  int solves = 0;
+
+  void launch_check() {
+    ++launches;
+#ifdef NSB_DEBUG_SYNC
+    CK(cudaStreamSynchronize(stream));
+#endif
+    CK(cudaGetLastError());
+  }
+};
+
+namespace {
+
+int fail(nsb_ctx* c, const std::string& m, int code = -1) {
+  if (c) c->err = m;
+  return code;
+}
+
+#define NSB_TRY try {
+#define NSB_CATCH(c)                                               \
+  }                                                                \
+  catch (const CudaErr& e) { return fail(c, e.msg); }              \
+  catch (const std::exception& e) { return fail(c, e.what()); }
+
+inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+
+// ---- halo exchange of one local vector (ghost tail refreshed from the owners) -----------
+void halo_exchange(nsb_ctx* c, double* v) {
+  if (c->nranks == 1) return;
+  const Structure& S = c->S;
+  // pack + grouped send/recv: ghosts are stored per owner contiguously, so receives land in place
+  auto& B = c->halo;
+  if (B.empty()) {
+    for (size_t k = 0; k < S.peer.size(); ++k) {
+      auto b = std::make_unique<HaloBuf>();
+      std::vector<int> uo(S.send_nodes[k].size()), po(S.send_pids[k].size());
+      for (size_t i = 0; i < uo.size(); ++i) uo[i] = (int)S.node_xoff(S.send_nodes[k][i]);
+      for (size_t i = 0; i < po.size(); ++i) po[i] = (int)S.pid_xoff(S.send_pids[k][i]);
+      b->uoff.upload(uo, c->stream); b->poff.upload(po, c->stream);
+      CK(cudaStreamSynchronize(c->stream));
+      b->u.alloc(uo.size() * S.dim); b->p.alloc(po.size());
+      B.push_back(std::move(b));
+    }
+  }
+  for (size_t k = 0; k < S.peer.size(); ++k) {
+    const int nu = (int)S.send_nodes[k].size(), np = (int)S.send_pids[k].size();
+    if (nu) { k_gather_nodes<<<nblk((long long)nu * S.dim, 256), 256, 0, c->stream>>>(nu, S.dim, B[k]->uoff.p, v, B[k]->u.p); c->launch_check(); }
+    if (np) { k_gather<<<nblk(np, 256), 256, 0, c->stream>>>(np, B[k]->poff.p, v, B[k]->p.p); c->launch_check(); }
+  }
+  CKN(ncclGroupStart());
+  long long uoff = S.n_own_dofs(), poff = S.n_own_dofs() + (long long)S.dim * S.nn_ghost;
+  for (size_t k = 0; k < S.peer.size(); ++k) {
+    const int peer = S.peer[k];
+    const size_t nu = S.send_nodes[k].size() * S.dim, np = S.send_pids[k].size();
+    if (nu) CKN(ncclSend(B[k]->u.p, nu, ncclDouble, peer, c->comm, c->stream));
+    if (np) CKN(ncclSend(B[k]->p.p, np, ncclDouble, peer, c->comm, c->stream));
+    const size_t ru = (size_t)S.recv_node_count[k] * S.dim, rp = (size_t)S.recv_pid_count[k];
+    if (ru) CKN(ncclRecv(v + uoff, ru, ncclDouble, peer, c->comm, c->stream));
+    if (rp) CKN(ncclRecv(v + poff, rp, ncclDouble, peer, c->comm, c->stream));
+    uoff += ru; poff += rp;
+  }
+  CKN(ncclGroupEnd());
+}
+
+void allreduce_sum(nsb_ctx* c, double* dbuf, int n) {
+  if (c->nranks == 1) return;
+  CKN(ncclAllReduce(dbuf, dbuf, n, ncclDouble, ncclSum, c->comm, c->stream));
+}
+
+// ---- templated launch helpers --------------------------------------------------------
+template <int DIM> void launch_assemble(nsb_ctx* c, bool newton) {
+  AsmParams P;
+  P.dt = c->par.dt; P.theta = c->par.theta; P.nu = c->par.nu; P.rho = c->par.rho;
+  P.use_supg = c->par.use_supg;
+  P.gamma = c->par.use_supg ? c->par.gamma : 0.0;
+  P.first_order_ustar = c->par.first_order_ustar;
+  const int stride = newton ? Ctx<DIM>::N_NEWTON : Ctx<DIM>::N_LIN;
+  if ((int)c->ctx_stride < stride) {
+    c->ctx.alloc((size_t)c->S.nc * stride);
+    c->ctx_stride = stride;
+  }
+  const double* vecA = newton ? c->v_cur.p : c->v_old.p;
+  const double* vecB = newton ? c->v_old.p : c->v_oldold.p;
+  size_t id = c->prof.begin(PC_ASM_CTX, c->stream);
+  if (newton)
+    k_cell_context<DIM, true><<<nblk(c->S.nc, ASM_WARPS), ASM_WARPS * 32, 0, c->stream>>>(c->M, P, vecA, vecB, c->ctx.p, c->cell_rhs.p);
+  else
+    k_cell_context<DIM, false><<<nblk(c->S.nc, ASM_WARPS), ASM_WARPS * 32, 0, c->stream>>>(c->M, P, vecA, vecB, c->ctx.p, c->cell_rhs.p);
+  c->launch_check();
+  c->prof.end(id, c->stream);
+  RowOut out{c->vals.p, c->v_rhs.p, c->dinv.p, nullptr};
+  id = c->prof.begin(PC_ASM_ROWS, c->stream);
+  if (newton)
+    k_node_rows<DIM, true><<<c->n_tiles, ASM_WARPS * 32, c->tile_smem_bytes, c->stream>>>(c->M, P, c->ctx.p, c->cell_rhs.p, c->cflag.p, c->cval.p, out, c->d_tile_ptr.p);
+  else
+    k_node_rows<DIM, false><<<c->n_tiles, ASM_WARPS * 32, c->tile_smem_bytes, c->stream>>>(c->M, P, c->ctx.p, c->cell_rhs.p, c->cflag.p, c->cval.p, out, c->d_tile_ptr.p);
+  c->launch_check();
+  c->prof.end(id, c->stream);
+}
+
+template <int DIM> void set_smem_attr(int bytes) {
+  CK(cudaFuncSetAttribute(k_node_rows<DIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CK(cudaFuncSetAttribute(k_node_rows<DIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+}
+
+// y(owned) = A x ; x must have a valid ghost tail
+void spmv_full(nsb_ctx* c, const double* x, double* y) {
+  size_t id = c->prof.begin(PC_SPMV, c->stream);
+  if (c->dim == 2) k_spmv_full<2, double><<<nblk(c->S.nn_own, SPMV_WARPS), SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, x, y);
+  else k_spmv_full<3, double><<<nblk(c->S.nn_own, SPMV_WARPS), SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, x, y);
+  c->launch_check();
+  c->prof.end(id, c->stream);
+}
+
+template <int MODE>
+void spmv_vel(nsb_ctx* c, const double* x, double* y, const double* r0, double* d, double c1, double c2) {
+  size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
+  const int g = nblk(c->S.nn_own, SPMV_WARPS);
+  if (c->dim == 2) k_spmv_vel<2, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, x, y, r0, d, c->dinv.p, c1, c2);
+  else k_spmv_vel<3, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, x, y, r0, d, c->dinv.p, c1, c2);
+  c->launch_check();
+  c->prof.end(id, c->stream);
+}
+
+double device_norm2(nsb_ctx* c, const double* x, long long n) {
+  const int nb = nblk(n, RED_CHUNK);
+  k_norm2_partial<<<nb, RED_THREADS, 0, c->stream>>>(x, n, c->partial.p);
+  c->launch_check();
+  k_reduce_partials<<<1, RED_THREADS, 0, c->stream>>>(nb, c->partial.p, c->d_nrm.p, 0);
+  c->launch_check();
+  allreduce_sum(c, c->d_nrm.p, 1);
+  double v = 0;
+  CK(cudaMemcpyAsync(&v, c->d_nrm.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return std::sqrt(v);
+}
+
+// ---- Chebyshev coefficients ------------------------------------------------------------
+struct Cheb {
+  double theta, delta, sigma, rho;
+  Cheb(double lmax, double lmin) : theta(0.5 * (lmax + lmin)), delta(0.5 * (lmax - lmin)) {
+    sigma = theta / delta;
+    rho = 1.0 / sigma;
+  }
+  // returns (c1, c2) of  d <- c1 d + c2 Dinv r  for step k >= 1 and advances rho
+  void next(double& c1, double& c2) {
+    const double rho_new = 1.0 / (2.0 * sigma - rho);
+    c1 = rho_new * rho;
+    c2 = 2.0 * rho_new / delta;
+    rho = rho_new;
+  }
+};
+
+// lambda_max(Dinv F) by power iteration (block-Jacobi scaled velocity block)
+void estimate_F_lmax(nsb_ctx* c, int iters) {
+  const long long nu = (long long)c->dim * c->S.nn_own;
+  if (!c->eig_init) {
+    std::vector<double> h(c->S.n_tot_dofs(), 0.0);
+    uint64_t s = 0x2545F4914F6CDD1Dull;
+    for (long long i = 0; i < nu; ++i) {
+      s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+      h[i] = (double)(s >> 11) / 9007199254740992.0 - 0.5;
+    }
+    c->eigv.upload(h, c->stream);
+    c->eig_init = true;
+  }
+  double lam = c->F_lmax;
+  for (int it = 0; it < iters; ++it) {
+    const double nv = device_norm2(c, c->eigv.p, nu);
+    if (!(nv > 0)) break;
+    k_axpby<<<nblk(nu, 256), 256, 0, c->stream>>>(nu, 0.0, c->eigv.p, 1.0 / nv, c->eigv.p);
+    c->launch_check();
+    halo_exchange(c, c->eigv.p);
+    spmv_vel<2>(c, c->eigv.p, c->w_tmp.p, nullptr, nullptr, 0, 0);
+    lam = device_norm2(c, c->w_tmp.p, nu);
+    CK(cudaMemcpyAsync(c->eigv.p, c->w_tmp.p, nu * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  c->F_lmax = lam;
+}
+
+// ---- pressure-space pieces (global, replicated vectors of length n_p) -------------------
+void csr_cheb(nsb_ctx* c, const DevCsr& A, const double* dinv, double lmax, double ratio, int degree,
+              const double* b, double* x, double* x2, double* d, bool zero_guess, double** result) {
+  // Jacobi-Chebyshev on A e = b (zero_guess) or continuing from x.  Ping-pongs x/x2.
+  Cheb ch(1.1 * lmax, 1.1 * lmax / ratio);
+  double* cur = x;
+  double* oth = x2;
+  int k0 = 0;
+  const int g8 = nblk((long long)A.n * 8, 256);
+  if (zero_guess) {
+    k_cheb_first<<<nblk(A.n, 256), 256, 0, c->stream>>>(A.n, dinv, b, d, cur, 1.0 / ch.theta);
+    c->launch_check();
+    k0 = 1;
+  }
+  for (int k = k0; k < degree; ++k) {
+    double c1, c2;
+    if (k == 0) { c1 = 0.0; c2 = 1.0 / ch.theta; }
+    else ch.next(c1, c2);
+    k_csr<3><<<g8, 256, 0, c->stream>>>(A, cur, oth, b, d, dinv, c1, c2);
+    c->launch_check();
+    std::swap(cur, oth);
+  }
+  *result = cur;
+}
+
+void amg_vcycle(nsb_ctx* c, int lev) {
+  // solves A_lev x = b_lev approximately; input levels[lev]->b, output pointer in levels[lev]->x (may swap with x2)
+  DevLevel& L = *c->amg[lev];
+  const int deg = c->opt.amg_smoother_degree;
+  if (lev + 1 == (int)c->amg.size()) {
+    if (c->coarse_n > 0) {
+      k_dense_mv<<<nblk((long long)L.n * 32, 256), 256, 0, c->stream>>>(L.n, c->coarse_inv.p, L.b.p, L.x.p);
+      c->launch_check();
+    } else {
+      double* res;
+      csr_cheb(c, L.A, L.dinv.p, L.lmax, 30.0, 12, L.b.p, L.x.p, L.x2.p, L.d.p, true, &res);
+      if (res != L.x.p) std::swap(L.x.p, L.x2.p);
+    }
+    return;
+  }
+  double* res;
+  csr_cheb(c, L.A, L.dinv.p, L.lmax, 20.0, deg, L.b.p, L.x.p, L.x2.p, L.d.p, true, &res);
+  if (res != L.x.p) std::swap(L.x.p, L.x2.p);
+  const int g8 = nblk((long long)L.n * 8, 256);
+  k_csr<1><<<g8, 256, 0, c->stream>>>(L.A, L.x.p, L.r.p, L.b.p, nullptr, nullptr, 0, 0);
+  c->launch_check();
+  DevLevel& N = *c->amg[lev + 1];
+  k_csr<0><<<nblk((long long)N.n * 8, 256), 256, 0, c->stream>>>(L.R, L.r.p, N.b.p, nullptr, nullptr, nullptr, 0, 0);
+  c->launch_check();
+  amg_vcycle(c, lev + 1);
+  k_csr<2><<<g8, 256, 0, c->stream>>>(L.P, N.x.p, L.x.p, nullptr, nullptr, nullptr, 0, 0);
+  c->launch_check();
+  csr_cheb(c, L.A, L.dinv.p, L.lmax, 20.0, deg, L.b.p, L.x.p, L.x2.p, L.d.p, false, &res);
+  if (res != L.x.p) std::swap(L.x.p, L.x2.p);
+}
+
+// ---- the block-triangular preconditioner (reference NavierStokes.hpp:320-344) -----------
+//   y0 = F~^-1 x0 ;  t = x1 - B y0 ;  y1 = -(rho/dt) Kp~^-1 t - cm Mp~^-1 t
+void precond_apply(nsb_ctx* c, const double* x, double* y) {
+  const Structure& S = c->S;
+  const int dim = c->dim;
+  const long long nu = (long long)dim * S.nn_own;
+  // --- step 1: block-Jacobi Chebyshev on F
+  const int deg = c->opt.cheb_degree_F;
+  Cheb ch(1.1 * c->F_lmax, 1.1 * c->F_lmax / c->opt.cheb_ratio_F);
+  double* z = c->w_z0.p;
+  double* zo = c->w_z1.p;
+  if (dim == 2) k_cheb_first_vel<2><<<nblk(S.nn_own, 256), 256, 0, c->stream>>>(S.nn_own, c->dinv.p, x, c->w_d.p, z, 1.0 / ch.theta);
+  else k_cheb_first_vel<3><<<nblk(S.nn_own, 256), 256, 0, c->stream>>>(S.nn_own, c->dinv.p, x, c->w_d.p, z, 1.0 / ch.theta);
+  c->launch_check();
+  for (int k = 1; k < deg; ++k) {
+    double c1, c2;
+    ch.next(c1, c2);
+    halo_exchange(c, z);
+    spmv_vel<1>(c, z, zo, x, c->w_d.p, c1, c2);
+    std::swap(z, zo);
+  }
+  CK(cudaMemcpyAsync(y, z, nu * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  // --- step 2: t = x1 - B y0
+  halo_exchange(c, z);
+  size_t id = c->prof.begin(PC_SCHUR, c->stream);
+  if (dim == 2) k_schur_rhs<2, double><<<nblk(S.np_own, SPMV_WARPS), SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, z, x, c->w_t.p);
+  else k_schur_rhs<3, double><<<nblk(S.np_own, SPMV_WARPS), SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, z, x, c->w_t.p);
+  c->launch_check();
+  c->prof.end(id, c->stream);
+  // --- step 3: Cahouet-Chabard Schur complement on the (replicated) pressure space
+  const double* tg = c->w_t.p;     // one rank: local pressure ids == global ids
+  id = c->prof.begin(PC_AMG, c->stream);
+  DevLevel& L0 = *c->amg[0];
+  CK(cudaMemcpyAsync(L0.b.p, tg, (size_t)L0.n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  amg_vcycle(c, 0);
+  double* mres;
+  csr_cheb(c, c->Mp, c->Mp_dinv.p, c->Mp_lmax, 6.0, c->opt.cheb_degree_Mp, tg, c->w_m0.p, c->w_m1.p, c->w_md.p, true, &mres);
+  double cm = c->opt.schur_mass_coeff;
+  if (cm < 0) cm = c->par.theta * c->par.nu + (c->par.use_supg ? c->par.gamma : 0.0);
+  k_lincomb<<<nblk(S.np_own, 256), 256, 0, c->stream>>>(S.np_own, -(c->par.rho / c->par.dt), L0.x.p, -cm, mres, y + nu);
+  c->launch_check();
+  c->prof.end(id, c->stream);
+}
+
+// ---- GMRES (SolverGMRES semantics) ---------------------------------------
+int gmres(nsb_ctx* c, int max_it, double tol_abs, int n_tmp, int* iterations, double* residual) {
+  const Structure& S = c->S;
+  const long long n = S.n_own_dofs();
+  const int m = std::max(1, n_tmp - 2);
+  if (c->V_cap < m + 1) {
+    c->V.alloc((size_t)(m + 1) * n);
+    c->V_cap = m + 1;
+  }
+  const int nb = nblk(n, RED_CHUNK);
+  if (c->partial.n < (size_t)nb * (m + 2)) c->partial.alloc((size_t)nb * (m + 2));
+  if (c->d_h.n < (size_t)2 * (m + 2)) c->d_h.alloc(2 * (m + 2));
+  double* x = c->v_sol.p;
+  CK(cudaMemsetAsync(x, 0, S.n_tot_dofs() * sizeof(double), c->stream));
+  std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), hcol(2 * (m + 2));
+  int it = 0;
+  double res = 0;
+  bool first = true;
+  for (;;) {
+    double* V0 = c->V.p;
+    if (first) {
+      precond_apply(c, c->v_rhs.p, c->w_in.p);
+    } else {
+      halo_exchange(c, x);
+      spmv_full(c, x, c->w_tmp.p);
+      k_lincomb<<<nblk(n, 256), 256, 0, c->stream>>>(n, 1.0, c->v_rhs.p, -1.0, c->w_tmp.p, c->w_tmp.p);
+      c->launch_check();
+      precond_apply(c, c->w_tmp.p, c->w_in.p);
+    }
+    const double beta = device_norm2(c, c->w_in.p, n);
+    res = beta;
+    if (first && beta <= tol_abs) { *iterations = 0; *residual = beta; return 0; }
+    first = false;
+    if (!(beta > 0)) { *iterations = it; *residual = beta; return 0; }
+    k_axpby<<<nblk(n, 256), 256, 0, c->stream>>>(n, 1.0 / beta, c->w_in.p, 0.0, V0);
+    c->launch_check();
+    std::fill(g.begin(), g.end(), 0.0);
+    g[0] = beta;
+    int kused = 0;
+    bool converged = false;
+    for (int k = 0; k < m; ++k) {
+      double* vk = c->V.p + (size_t)k * n;
+      double* w = c->V.p + (size_t)(k + 1) * n;
+      // w = P^-1 A v_k
+      const double* xin = vk;
+      if (c->nranks > 1) {
+        CK(cudaMemcpyAsync(c->w_pin.p, vk, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        halo_exchange(c, c->w_pin.p);
+        xin = c->w_pin.p;
+      }
+      spmv_full(c, xin, c->w_tmp.p);
+      precond_apply(c, c->w_tmp.p, w);
+      // classical Gram-Schmidt (twice): h = V^T w ; w -= V h
+      size_t id = c->prof.begin(PC_ORTH, c->stream);
+      const int passes = c->opt.reorthogonalize ? 2 : 1;
+      for (int pass = 0; pass < passes; ++pass) {
+        k_multi_dot<<<nb, RED_THREADS, 0, c->stream>>>(k + 1, c->V.p, n, w, n, c->partial.p);
+        c->launch_check();
+        double* hp = c->d_h.p + pass * (m + 2);
+        k_reduce_partials<<<k + 1, RED_THREADS, 0, c->stream>>>(nb, c->partial.p, hp, 0);
+        c->launch_check();
+        allreduce_sum(c, hp, k + 1);
+        k_multi_axpy<<<nb, RED_THREADS, 0, c->stream>>>(k + 1, c->V.p, n, hp, -1.0, w, n, (pass == passes - 1) ? c->partial.p : nullptr);
+        c->launch_check();
+      }
+      k_reduce_partials<<<1, RED_THREADS, 0, c->stream>>>(nb, c->partial.p, c->d_nrm.p, 0);
+      c->launch_check();
+      allreduce_sum(c, c->d_nrm.p, 1);
+      k_scale_by_inv_norm<<<nblk(n, 256), 256, 0, c->stream>>>(n, w, c->d_nrm.p, w);
+      c->launch_check();
+      c->prof.end(id, c->stream);
+      double nrm2 = 0;
+      CK(cudaMemcpyAsync(hcol.data(), c->d_h.p, sizeof(double) * 2 * (m + 2), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(&nrm2, c->d_nrm.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      for (int i = 0; i <= k; ++i) H[(size_t)i * m + k] = hcol[i] + (passes == 2 ? hcol[(m + 2) + i] : 0.0);
+      H[(size_t)(k + 1) * m + k] = std::sqrt(nrm2);
+      // Givens
+      for (int i = 0; i < k; ++i) {
+        const double t = cs[i] * H[(size_t)i * m + k] + sn[i] * H[(size_t)(i + 1) * m + k];
+        H[(size_t)(i + 1) * m + k] = -sn[i] * H[(size_t)i * m + k] + cs[i] * H[(size_t)(i + 1) * m + k];
+        H[(size_t)i * m + k] = t;
+      }
+      const double a = H[(size_t)k * m + k], b = H[(size_t)(k + 1) * m + k];
+      const double dd = std::hypot(a, b);
+      cs[k] = a / dd; sn[k] = b / dd;
+      H[(size_t)k * m + k] = dd;
+      H[(size_t)(k + 1) * m + k] = 0.0;
+      g[k + 1] = -sn[k] * g[k];
+      g[k] = cs[k] * g[k];
+      res = std::fabs(g[k + 1]);
+      ++it;
+      kused = k + 1;
+      if (res <= tol_abs) { converged = true; break; }
+      if (it >= max_it) break;
+      if (!(nrm2 > 0)) break;       // lucky breakdown
+    }
+    // x += V y
+    std::vector<double> yv(kused);
+    for (int i = kused - 1; i >= 0; --i) {
+      double s = g[i];
+      for (int j = i + 1; j < kused; ++j) s -= H[(size_t)i * m + j] * yv[j];
+      yv[i] = s / H[(size_t)i * m + i];
+    }
+    CK(cudaMemcpyAsync(c->d_h.p, yv.data(), sizeof(double) * kused, cudaMemcpyHostToDevice, c->stream));
+    k_multi_axpy<<<nb, RED_THREADS, 0, c->stream>>>(kused, c->V.p, n, c->d_h.p, 1.0, x, n, nullptr);
+    c->launch_check();
+    CK(cudaStreamSynchronize(c->stream));
+    if (converged || it >= max_it) {
+      *iterations = it;
+      *residual = res;
+      return converged ? 0 : 1;
+    }
+  }
+}
+
+void build_tiles(nsb_ctx* c) {
+  const Structure& S = c->S;
+  int dev_max = 0;
+  CK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+  const int stat = 16 * 1024;      // static shared memory of k_node_rows (upper bound)
+  int budget = std::max(S.max_node_smem_doubles, 5 * 1024);      // doubles: >= 40 KB
+  if ((long long)budget * 8 + stat > dev_max)
+    throw CudaErr{"a node's rows do not fit in shared memory (valence too high)"};
+  std::vector<int> tp;
+  tp.push_back(0);
+  int sum = 0, cnt = 0;
+  for (int A = 0; A < S.nn_own; ++A) {
+    const int need = (S.dim + (S.node_pid[A] >= 0 ? 1 : 0)) * S.row_len(A);
+    if (cnt > 0 && (sum + need > budget || cnt >= 64)) { tp.push_back(A); sum = 0; cnt = 0; }
+    sum += need; ++cnt;
+  }
+  tp.push_back(S.nn_own);
+  c->n_tiles = (int)tp.size() - 1;
+  c->tile_smem_bytes = budget * 8;
+  c->d_tile_ptr.upload(tp, c->stream);
+  if (c->dim == 2) set_smem_attr<2>(c->tile_smem_bytes);
+  else set_smem_attr<3>(c->tile_smem_bytes);
+}
+
+// one-time M_p, K_p on the host over the GLOBAL P1 graph (reference cpp:798-803, 812-829)
+void host_pressure_matrices(nsb_ctx* c, const std::vector<unsigned char>& pflag) {
+  const int dim = c->dim, NV = dim + 1;
+  const int64_t np = c->n_p, C = c->n_cells;
+  FeTables T;
+  fill_tables(dim, T);
+  double wsum = 0;
+  for (int q = 0; q < T.nq; ++q) wsum += T.w[q];
+  // P1 graph
+  std::vector<std::vector<int>> adj(np);
+  for (int64_t cc = 0; cc < C; ++cc)
+    for (int i = 0; i < NV; ++i)
+      for (int j = 0; j < NV; ++j) adj[c->g_cell_pid[cc * NV + i]].push_back(c->g_cell_pid[cc * NV + j]);
+  HostCsr Mp, Kp;
+  Mp.n = Mp.m = (int)np;
+  Mp.ptr.assign(np + 1, 0);
+  for (int64_t i = 0; i < np; ++i) {
+    auto& a = adj[i];
+    std::sort(a.begin(), a.end());
+    a.erase(std::unique(a.begin(), a.end()), a.end());
+    Mp.ptr[i + 1] = Mp.ptr[i] + (int)a.size();
+  }
+  Mp.col.resize(Mp.ptr[np]);
+  for (int64_t i = 0; i < np; ++i) std::copy(adj[i].begin(), adj[i].end(), Mp.col.begin() + Mp.ptr[i]);
+  Mp.val.assign(Mp.col.size(), 0.0);
+  Kp = Mp;
+  auto find = [&](int r, int col) {
+    const int* b = Mp.col.data() + Mp.ptr[r];
+    const int* e = Mp.col.data() + Mp.ptr[r + 1];
+    return (int)(std::lower_bound(b, e, col) - Mp.col.data());
+  };
+  for (int64_t cc = 0; cc < C; ++cc) {
+    const uint32_t* cv = c->cell_vertices.data() + cc * NV;
+    double X[4][3] = {{0}};
+    for (int v = 0; v < NV; ++v)
+      for (int k = 0; k < dim; ++k) X[v][k] = c->coords[(size_t)cv[v] * dim + k];
+    double gl[4][3] = {{0}}, det;
+    if (dim == 2) {
+      const double a = X[1][0] - X[0][0], b = X[2][0] - X[0][0], cq = X[1][1] - X[0][1], d = X[2][1] - X[0][1];
+      det = a * d - b * cq;
+      gl[1][0] = d / det; gl[1][1] = -b / det; gl[2][0] = -cq / det; gl[2][1] = a / det;
+      for (int k = 0; k < 2; ++k) gl[0][k] = -(gl[1][k] + gl[2][k]);
+    } else {
+      double J[3][3];
+      for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 3; ++k) J[r][k] = X[k + 1][r] - X[0][r];
+      const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
+                   c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+      det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+      const double id = 1.0 / det;
+      gl[1][0] = c00 * id; gl[1][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id; gl[1][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+      gl[2][0] = c01 * id; gl[2][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id; gl[2][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+      gl[3][0] = c02 * id; gl[3][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id; gl[3][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+      for (int k = 0; k < 3; ++k) gl[0][k] = -((gl[1][k] + gl[2][k]) + gl[3][k]);
+    }
+    const double absJ = std::fabs(det);
+    const int* pid = c->g_cell_pid.data() + cc * NV;
+    for (int i = 0; i < NV; ++i) {
+      const bool ci = pflag[pid[i]] != 0;
+      for (int j = 0; j < NV; ++j) {
+        const bool cj = pflag[pid[j]] != 0;
+        double gg = 0;
+        for (int k = 0; k < dim; ++k) gg += gl[i][k] * gl[j][k];
+        double m = absJ * T.MPhat[i][j], kk = absJ * wsum * gg;
+        if (ci || cj) {
+          if (i == j) { m = std::fabs(m); kk = std::fabs(kk); }    // constrained diagonal: |m_cc| (A.5)
+          else { m = 0; kk = 0; }
+        }
+        const int p = find(pid[i], pid[j]);
+        Mp.val[p] += m;
+        Kp.val[p] += kk;
+      }
+    }
+  }
+  for (size_t k = 0; k < Kp.val.size(); ++k) Kp.val[k] += 1e-6 * Mp.val[k];     // cpp:536, 828
+  c->h_Mp = std::move(Mp);
+  c->h_Kp = std::move(Kp);
+}
+
+double* vec_ptr(nsb_ctx* c, int which) {
+  switch (which) {
+    case NSB_SOLUTION_OLD: return c->v_old.p;
+    case NSB_SOLUTION_OLD_OLD: return c->v_oldold.p;
+    case NSB_CURRENT_SOLUTION: return c->v_cur.p;
+    case NSB_SOLUTION: return c->v_sol.p;
+    case NSB_RHS: return c->v_rhs.p;
+  }
+  return nullptr;
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+int nsb_create(int dim, int device, nsb_handle* out) {
+  if (!out) return -1;
+  *out = nullptr;
+  if (dim != 2 && dim != 3) return -1;
+  nsb_ctx* c = new nsb_ctx();
+  c->dim = dim; c->device = device;
+  *out = c;
+  NSB_TRY
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) throw CudaErr{"no such CUDA device (the product path has no CPU fallback)"};
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) throw CudaErr{"nsb200 is built for sm_100a (B200) only"};
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&c->t0));
+  CK(cudaEventCreate(&c->t1));
+  FeTables T2, T3;
+  fill_tables(2, T2);
+  fill_tables(3, T3);
+  CK(cudaMemcpyToSymbol(c_fe2, &T2, sizeof(FeTables)));
+  CK(cudaMemcpyToSymbol(c_fe3, &T3, sizeof(FeTables)));
+  c->opt.cheb_degree_F = 3; c->opt.cheb_ratio_F = 30.0; c->opt.cheb_degree_Mp = 3;
+  c->opt.amg_smoother_degree = 2; c->opt.schur_mass_coeff = -1.0; c->opt.reorthogonalize = 1;
+  c->par.dt = 0.01; c->par.theta = 1.0; c->par.nu = 1e-3; c->par.rho = 1.0; c->par.gamma = 0.1;
+  c->d_nrm.alloc(4);
+  return 0;
+  NSB_CATCH(c)
+}
+
+int nsb_destroy(nsb_handle c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm) ncclCommDestroy(c->comm);
+  if (c->t0) cudaEventDestroy(c->t0);
+  if (c->t1) cudaEventDestroy(c->t1);
+  cudaStream_t s = c->stream;
+  delete c;
+  if (s) cudaStreamDestroy(s);
+  return 0;
+}
+
+const char* nsb_last_error(nsb_handle c) { return c ? c->err.c_str() : "null handle"; }
+
+int nsb_comm_unique_id(void* out128) {
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return -1;
+  std::memcpy(out128, &id, sizeof(id));
+  return 0;
+}
+
+int nsb_comm_init(nsb_handle c, int rank, int nranks, const void* uid) {
+  if (!c) return -1;
+  NSB_TRY
+  CK(cudaSetDevice(c->device));
+  if (c->have_mesh) throw CudaErr{"nsb_comm_init must precede nsb_upload_mesh"};
+  if (nranks > 1) {
+    ncclUniqueId id;
+    std::memcpy(&id, uid, sizeof(id));
+    CKN(ncclCommInitRank(&c->comm, nranks, id, rank));
+  }
+  c->rank = rank; c->nranks = nranks;
+  return 0;
+  NSB_CATCH(c)
+}
+
+int nsb_upload_mesh(nsb_handle c, int64_t n_vertices, const double* coords, int64_t n_cells,
+                    const uint32_t* cell_vertices, const uint32_t* cell_dofs, int64_t n_u, int64_t n_p,
+                    const int32_t* cell_part) {
+  if (!c) return -1;
+  NSB_TRY
+  CK(cudaSetDevice(c->device));
+  const int dim = c->dim, NV = dim + 1;
+  std::string e = build_structure(dim, n_vertices, coords, n_cells, cell_vertices, cell_dofs, n_u, n_p,
+                                  c->nranks > 1 ? cell_part : nullptr, c->rank, c->nranks, c->S);
+  if (!e.empty()) return fail(c, e);
+  if (c->nranks > 1 && !cell_part) return fail(c, "cell_part is required with more than one rank");
+  Structure& S = c->S;
+  c->n_vertices = n_vertices; c->n_cells = n_cells; c->n_u = n_u; c->n_p = n_p;
+  c->coords.assign(coords, coords + n_vertices * dim);
+  c->cell_vertices.assign(cell_vertices, cell_vertices + n_cells * NV);
+  c->g_cell_pid.resize(n_cells * NV);
+  const int DPC = S.DPC;
+  for (int64_t cc = 0; cc < n_cells; ++cc)
+    for (int v = 0; v < NV; ++v) c->g_cell_pid[cc * NV + v] = (int)(cell_dofs[cc * DPC + v * (dim + 1) + dim] - n_u);
+  if (S.n_tot_dofs() >= (int64_t)INT32_MAX) return fail(c, "local vector too long for 32-bit offsets");
+  // global dof -> local offset
+  c->g2x.assign(n_u + n_p, -1);
+  for (int A = 0; A < S.nn_own + S.nn_ghost; ++A)
+    for (int k = 0; k < dim; ++k) c->g2x[S.node_gid[A] * dim + k] = (int)S.node_xoff(A) + k;
+  for (int P = 0; P < S.np_own + S.np_ghost; ++P) c->g2x[n_u + S.pid_gid[P]] = (int)S.pid_xoff(P);
+  // ---- device copies
+  cudaStream_t st = c->stream;
+  std::vector<int> cx(S.cell_nodes.size()), cp(S.cell_pids.size());
+  for (size_t i = 0; i < cx.size(); ++i) cx[i] = (int)S.node_xoff(S.cell_nodes[i]);
+  for (size_t i = 0; i < cp.size(); ++i) cp[i] = (int)S.pid_xoff(S.cell_pids[i]);
+  c->d_cell_xoff.upload(cx, st); c->d_cell_poff.upload(cp, st);
+  c->d_cell_geom.upload(S.cell_geom, st);
+  c->d_rank_uu.upload(S.rank_uu, st); c->d_rank_up.upload(S.rank_up, st);
+  std::vector<int> nx(S.nbr.size()), px(S.pnbr.size());
+  for (size_t i = 0; i < nx.size(); ++i) nx[i] = (int)S.node_xoff(S.nbr[i]);
+  for (size_t i = 0; i < px.size(); ++i) px[i] = (int)S.pid_xoff(S.pnbr[i]);
+  c->d_nbr_xoff.upload(nx, st); c->d_pnbr_xoff.upload(px, st);
+  std::vector<long long> t64;
+  auto up64 = [&](const std::vector<int64_t>& v, DBuf<long long>& d) {
+    t64.assign(v.begin(), v.end());
+    d.upload(t64, st);
+    CK(cudaStreamSynchronize(st));
+  };
+  up64(S.nbr_ptr, c->d_nbr_ptr); up64(S.pnbr_ptr, c->d_pnbr_ptr);
+  up64(S.rowbase, c->d_rowbase); up64(S.prowbase, c->d_prowbase); up64(S.n2c_ptr, c->d_n2c_ptr);
+  c->d_selfrank.upload(S.selfrank, st);
+  std::vector<int> npid(S.node_pid.begin(), S.node_pid.begin() + S.nn_own);
+  c->d_node_pid.upload(npid, st);
+  std::vector<int> pnode(S.pid_node.begin(), S.pid_node.begin() + S.np_own);
+  c->d_pid_node.upload(pnode, st);
+  c->d_pselfrank.upload(S.pselfrank, st);
+  c->d_n2c.upload(S.n2c, st);
+  CK(cudaStreamSynchronize(st));
+  DevMesh& M = c->M;
+  M.dim = dim; M.nn_own = S.nn_own; M.nn_tot = S.nn_own + S.nn_ghost; M.np_own = S.np_own;
+  M.np_tot = S.np_own + S.np_ghost; M.nc = S.nc; M.n_own = S.n_own_dofs(); M.n_tot = S.n_tot_dofs();
+  M.cell_xoff = c->d_cell_xoff.p; M.cell_poff = c->d_cell_poff.p; M.cell_geom = c->d_cell_geom.p;
+  M.rank_uu = c->d_rank_uu.p; M.rank_up = c->d_rank_up.p;
+  M.nbr_ptr = c->d_nbr_ptr.p; M.nbr_xoff = c->d_nbr_xoff.p; M.pnbr_ptr = c->d_pnbr_ptr.p; M.pnbr_xoff = c->d_pnbr_xoff.p;
+  M.selfrank = c->d_selfrank.p; M.node_pid = c->d_node_pid.p; M.pid_node = c->d_pid_node.p; M.pselfrank = c->d_pselfrank.p;
+  M.rowbase = c->d_rowbase.p; M.prowbase = c->d_prowbase.p; M.n2c_ptr = c->d_n2c_ptr.p; M.n2c = c->d_n2c.p;
+  build_tiles(c);
+  // vectors and system storage
+  const size_t nt = (size_t)S.n_tot_dofs();
+  for (DBuf<double>* v : {&c->v_old, &c->v_oldold, &c->v_cur, &c->v_sol, &c->v_rhs, &c->cval, &c->w_z0, &c->w_z1, &c->w_d,
+                          &c->w_in, &c->w_tmp, &c->w_pin}) {
+    v->alloc(nt);
+    v->zero(st);
+  }
+  c->cflag.alloc(nt); c->cflag.zero(st);
+  c->vals.alloc((size_t)S.nnz_local);
+  c->dinv.alloc((size_t)S.nn_own * dim * dim);
+  c->cell_rhs.alloc((size_t)S.nc * S.DPC);
+  c->ctx_stride = 0;
+  c->partial.alloc((size_t)nblk(S.n_own_dofs(), RED_CHUNK) * 4);
+  CK(cudaStreamSynchronize(st));
+  c->have_mesh = true; c->have_matrix = false; c->have_pressure = false;
+  c->eig_init = false; c->F_lmax = 0; c->solves = 0; c->V_cap = 0;
+  return 0;
+  NSB_CATCH(c)
+}
+
+int nsb_get_sizes(nsb_handle c, int64_t* nrows, int64_t* nnz, int64_t* ncl) {
+  if (!c || !c->have_mesh) return fail(c, "no mesh uploaded");
+  if (nrows) *nrows = c->S.n_own_dofs();
+  if (nnz) *nnz = c->S.nnz_local;
+  if (ncl) *ncl = c->S.nc;
+  return 0;
+}
+
+int nsb_get_pattern(nsb_handle c, int64_t* rowptr, uint32_t* col) {
+  if (!c || !c->have_mesh) return fail(c, "no mesh uploaded");
+  std::vector<int64_t> rp;
+  std::vector<uint32_t> cl;
+  export_pattern(c->S, rp, cl);
+  std::copy(rp.begin(), rp.end(), rowptr);
+  std::copy(cl.begin(), cl.end(), col);
+  return 0;
+}
+
+int nsb_get_row_gids(nsb_handle c, int64_t* gid) {
+  if (!c || !c->have_mesh) return fail(c, "no mesh uploaded");
+  std::vector<int64_t> g;
+  export_row_gids(c->S, g);
+  std::copy(g.begin(), g.end(), gid);
+  return 0;
+}
+
+int nsb_set_constraints(nsb_handle c, int64_t n, const uint32_t* dof, const double* val) {
+  if (!c || !c->have_mesh) return fail(c, "no mesh uploaded");
+  NSB_TRY
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  // clear the previous set
+  if (c->n_con) {
+    k_scatter_flags<<<nblk(c->n_con, 256), 256, 0, st>>>(c->n_con, c->c_idx.p, c->cflag.p, 0);
+    c->launch_check();
+  }
+  std::vector<int> idx;
+  std::vector<double> v;
+  idx.reserve(n); v.reserve(n);
+  const int64_t N = c->n_u + c->n_p;
+  for (int64_t i = 0; i < n; ++i) {
+    if (dof[i] >= N) return fail(c, "constraint DoF out of range");
+    const int x = c->g2x[dof[i]];
+    if (x >= 0) { idx.push_back(x); v.push_back(val[i]); }
+  }
+  c->n_con = (int)idx.size();
+  CK(cudaStreamSynchronize(st));
+  c->c_idx.upload(idx, st);
+  c->c_val.upload(v, st);
+  if (c->n_con) {
+    k_scatter_flags<<<nblk(c->n_con, 256), 256, 0, st>>>(c->n_con, c->c_idx.p, c->cflag.p, 1);
+    c->launch_check();
+    k_scatter_vals<<<nblk(c->n_con, 256), 256, 0, st>>>(c->n_con, c->c_idx.p, c->c_val.p, c->cval.p);
+    c->launch_check();
+  }
+  CK(cudaStreamSynchronize(st));
+  return 0;
+  NSB_CATCH(c)
+}
+
+int nsb_set_params(nsb_handle c, const nsb_params* p) {
+  if (!c || !p) return -1;
+  if (!(p->dt > 0)) return fail(c, "dt must be positive");
+  c->par = *p;
+  return 0;
+}
+
+int nsb_set_solver_opts(nsb_handle c, const nsb_solver_opts* o) {
+  if (!c || !o) return -1;
+  nsb_solver_opts n = *o;
+  if (n.cheb_degree_F <= 0) n.cheb_degree_F = 3;
+  if (!(n.cheb_ratio_F > 1)) n.cheb_ratio_F = 30.0;
+  if (n.cheb_degree_Mp <= 0) n.cheb_degree_Mp = 3;
+  if (n.amg_smoother_degree <= 0) n.amg_smoother_degree = 2;
+  if (n.schur_mass_coeff == 0.0) n.schur_mass_coeff = -1.0;
+  c->opt = n;
+  return 0;
+}
+
+int nsb_set_vector(nsb_handle c, int which, const double* vg) {
+  if (!c || !c->have_mesh) return fail(c, "no mesh uploaded");
+  NSB_TRY
+  CK(cudaSetDevice(c->device));
+  double* d = vec_ptr(c, which);
+  if (!d) return fail(c, "bad vector id");
+  const Structure& S = c->S;
+  std::vector<double> loc(S.n_tot_dofs());
+  const int dim = c->dim;
+  for (int A = 0; A < S.nn_own + S.nn_ghost; ++A)
+    for (int k = 0; k < dim; ++k) loc[S.node_xoff(A) + k] = vg[S.node_gid[A] * dim + k];
+  for (int P = 0; P < S.np_own + S.np_ghost; ++P) loc[S.pid_xoff(P)] = vg[c->n_u + S.pid_gid[P]];
+  CK(cudaMemcpyAsync(d, loc.data(), loc.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+  NSB_CATCH(c)
+}
+
+int nsb_get_vector(nsb_handle c, int which, double* vg) {
+  if (!c || !c->have_mesh) return fail(c, "no mesh uploaded");
+  NSB_TRY
+  CK(cudaSetDevice(c->device));
+  double* d = vec_ptr(c, which);
+  if (!d) return fail(c, "bad vector id");
+  const Structure& S = c->S;
+  std::vector<double> loc(S.n_own_dofs());
+  CK(cudaMemcpyAsync(loc.data(), d, loc.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const int dim = c->dim;
+  for (int A = 0; A < S.nn_own; ++A)
+    for (int k = 0; k < dim; ++k) vg[S.node_gid[A] * dim + k] = loc[(size_t)dim * A + k];
+  for (int P = 0; P < S.np_own; ++P) vg[c->n_u + S.pid_gid[P]] = loc[(size_t)dim * S.nn_own + P];
+  return 0;
+  NSB_CATCH(c)
+}
+
+int nsb_copy_vector(nsb_handle c, int dst, int src) {
+  if (!c || !c->have_mesh) return fail(c, "no mesh uploaded");
+  NSB_TRY
+  CK(cudaSetDevice(c->device));
+  double *d = vec_ptr(c, dst), *s = vec_ptr(c, src);
+  if (!d || !s) return fail(c, "bad vector id");
+  CK(cudaMemcpyAsync(d, s, c->S.n_own_dofs() * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  halo_exchange(c, d);
+  return 0;
+  NSB_CATCH(c)
+}
+
+int nsb_axpy_vector(nsb_handle c, int dst, double alpha, int src) {
+  if (!c || !c->have_mesh) return fail(c, "no mesh uploaded");
+  NSB_TRY
+  CK(cudaSetDevice(c->device));
+  double *d = vec_ptr(c, dst), *s = vec_ptr(c, src);
+  if (!d || !s) return fail(c, "bad vector id");
+  const long long n = c->S.n_own_dofs();
+  k_axpby<<<nblk(n, 256), 256, 0, c->stream>>>(n, alpha, s, 1.0, d);
+  c->launch_check();
+  halo_exchange(c, d);
+  return 0;
+  NSB_CATCH(c)
+}
+
+static int assemble_common(nsb_handle c, bool newton) {
+  if (!c || !c->have_mesh) return fail(c, "no mesh uploaded");
+  NSB_TRY
+  CK(cudaSetDevice(c->device));
+  if (c->dim == 2) launch_assemble<2>(c, newton);
+  else launch_assemble<3>(c, newton);
+  c->have_matrix = true;
+  return 0;
+  NSB_CATCH(c)
+}
+
+int nsb_assemble_linearized(nsb_handle c) { return assemble_common(c, false); }
+int nsb_assemble_newton(nsb_handle c) { return assemble_common(c, true); }
+
+int nsb_assemble_pressure_matrices(nsb_handle c) {
+  if (!c || !c->have_mesh) return fail(c, "no mesh uploaded");
+  NSB_TRY
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  // pressure constraint flags in GLOBAL pressure numbering, from the current constraint set
+  std::vector<unsigned char> pflag(c->n_p, 0);
+  {
+    std::vector<unsigned char> lf(c->S.n_tot_dofs());
+    CK(cudaMemcpyAsync(lf.data(), c->cflag.p, lf.size(), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int P = 0; P < c->S.np_own + c->S.np_ghost; ++P) pflag[c->S.pid_gid[P]] = lf[c->S.pid_xoff(P)];
+    if (c->nranks > 1) {
+      // merge flags across ranks (max) through a small device buffer
+      DBuf<double> tmp;
+      std::vector<double> f(pflag.begin(), pflag.end());
+      tmp.upload(f, st);
+      CKN(ncclAllReduce(tmp.p, tmp.p, f.size(), ncclDouble, ncclMax, c->comm, st));
+      CK(cudaMemcpyAsync(f.data(), tmp.p, f.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      for (size_t i = 0; i < f.size(); ++i) pflag[i] = f[i] != 0.0;
+    }
+  }
+  host_pressure_matrices(c, pflag);
+  // M_p on the device + Jacobi data
+  upload_csr(c->h_Mp, c->Mp_ptr, c->Mp_col, c->Mp_val, c->Mp, st);
+  std::vector<double> md(c->h_Mp.n);
+  for (int i = 0; i < c->h_Mp.n; ++i)
+    for (int k = c->h_Mp.ptr[i]; k < c->h_Mp.ptr[i + 1]; ++k)
+      if (c->h_Mp.col[k] == i) md[i] = 1.0 / c->h_Mp.val[k];
+  c->Mp_lmax = power_lmax_jacobi(c->h_Mp, md);
+  c->Mp_dinv.upload(md, st);
+  // multigrid hierarchy of K_p
+  AmgHierarchy H;
+  amg_setup(c->h_Kp, H);
+  c->amg.clear();
+  for (auto& L : H.levels) {
+    auto D = std::make_unique<DevLevel>();
+    D->n = L.A.n;
+    D->lmax = L.lmax;
+    upload_csr(L.A, D->Aptr, D->Acol, D->Aval, D->A, st);
+    if (L.P.n) {
+      upload_csr(L.P, D->Pptr, D->Pcol, D->Pval, D->P, st);
+      upload_csr(L.R, D->Rptr, D->Rcol, D->Rval, D->R, st);
+    }
+    D->dinv.upload(L.dinv, st);
+    for (DBuf<double>* v : {&D->x, &D->x2, &D->b, &D->d, &D->r}) { v->alloc(L.A.n); v->zero(st); }
+    c->amg.push_back(std::move(D));
+  }
+  c->coarse_n = 0;
+  if (!H.coarse_inv.empty()) {
+    c->coarse_inv.upload(H.coarse_inv, st);
+    c->coarse_n = H.levels.back().A.n;
+  }
+  const size_t np = (size_t)c->n_p;
+  for (DBuf<double>* v : {&c->w_t, &c->w_y1, &c->w_m0, &c->w_m1, &c->w_md}) { v->alloc(np); v->zero(st); }
+  CK(cudaStreamSynchronize(st));
+  c->have_pressure = true;
+  return 0;
+  NSB_CATCH(c)
+}
+
+int nsb_rhs_norm(nsb_handle c, double* norm) {
+  if (!c || !c->have_matrix) return fail(c, "no assembled system");
+  NSB_TRY
+  CK(cudaSetDevice(c->device));
+  *norm = device_norm2(c, c->v_rhs.p, c->S.n_own_dofs());
+  return 0;
+  NSB_CATCH(c)
+}
+
+int nsb_solve(nsb_handle c, int max_it, double tol_rel, int n_tmp, int* iterations, double* residual) {
+  if (!c || !c->have_matrix) return fail(c, "no assembled system");
+  if (!c->have_pressure) return fail(c, "nsb_assemble_pressure_matrices has not been called");
+  if (c->nranks > 1) return fail(c, "multi-GPU Schur-complement gather is not wired yet");
+  NSB_TRY
+  CK(cudaSetDevice(c->device));
+  int it = 0;
+  double res = 0;
+  // eigenvalue bound of the block-Jacobi scaled velocity block: full estimate once, cheap refresh after
+  estimate_F_lmax(c, c->solves == 0 ? 20 : 2);
+  const double bnorm = device_norm2(c, c->v_rhs.p, c->S.n_own_dofs());
+  const int rc = gmres(c, max_it, tol_rel * bnorm, n_tmp > 2 ? n_tmp : 150, &it, &res);
+  // constraints.distribute(x)   (cpp:566, 862)
+  if (c->n_con) {
+    k_scatter_vals<<<nblk(c->n_con, 256), 256, 0, c->stream>>>(c->n_con, c->c_idx.p, c->c_val.p, c->v_sol.p);
+    c->launch_check();
+  }
+  halo_exchange(c, c->v_sol.p);
+  CK(cudaStreamSynchronize(c->stream));
+  ++c->solves;
+  if (iterations) *iterations = it;
+  if (residual) *residual = res;
+  return rc;
+  NSB_CATCH(c)
+}
+
+int nsb_get_matrix_values(nsb_handle c, double* vals) {
+  if (!c || !c->have_matrix) return fail(c, "no assembled system");
+  NSB_TRY
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(vals, c->vals.p, (size_t)c->S.nnz_local * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+  NSB_CATCH(c)
+}
+
+int nsb_get_pressure_matrix(nsb_handle c, int which, int64_t* n, int64_t* nnz, int32_t* rowptr, int32_t* col, double* val) {
+  if (!c || !c->have_pressure) return fail(c, "pressure matrices not assembled");
+  const HostCsr& A = which == 0 ? c->h_Mp : c->h_Kp;
+  if (n) *n = A.n;
+  if (nnz) *nnz = A.nnz();
+  if (rowptr) std::copy(A.ptr.begin(), A.ptr.end(), rowptr);
+  if (col) std::copy(A.col.begin(), A.col.end(), col);
+  if (val) std::copy(A.val.begin(), A.val.end(), val);
+  return 0;
+}
+
+int nsb_spmv(nsb_handle c, const double* xg, double* yg) {
+  if (!c || !c->have_matrix) return fail(c, "no assembled system");
+  NSB_TRY
+  CK(cudaSetDevice(c->device));
+  const Structure& S = c->S;
+  std::vector<double> loc(S.n_tot_dofs());
+  const int dim = c->dim;
+  for (int A = 0; A < S.nn_own + S.nn_ghost; ++A)
+    for (int k = 0; k < dim; ++k) loc[S.node_xoff(A) + k] = xg[S.node_gid[A] * dim + k];
+  for (int P = 0; P < S.np_own + S.np_ghost; ++P) loc[S.pid_xoff(P)] = xg[c->n_u + S.pid_gid[P]];
+  CK(cudaMemcpyAsync(c->w_pin.p, loc.data(), loc.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  spmv_full(c, c->w_pin.p, c->w_tmp.p);
+  std::vector<double> out(S.n_own_dofs());
+  CK(cudaMemcpyAsync(out.data(), c->w_tmp.p, out.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int A = 0; A < S.nn_own; ++A)
+    for (int k = 0; k < dim; ++k) yg[S.node_gid[A] * dim + k] = out[(size_t)dim * A + k];
+  for (int P = 0; P < S.np_own; ++P) yg[c->n_u + S.pid_gid[P]] = out[(size_t)dim * S.nn_own + P];
+  return 0;
+  NSB_CATCH(c)
+}
+
+int nsb_timer_start(nsb_handle c) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  return cudaEventRecord(c->t0, c->stream) == cudaSuccess ? 0 : -1;
+}
+int nsb_timer_stop(nsb_handle c, double* ms) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  cudaEventRecord(c->t1, c->stream);
+  cudaEventSynchronize(c->t1);
+  float t = 0;
+  cudaEventElapsedTime(&t, c->t0, c->t1);
+  if (ms) *ms = t;
+  return 0;
+}
+int nsb_synchronize(nsb_handle c) {
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  return cudaStreamSynchronize(c->stream) == cudaSuccess ? 0 : fail(c, "stream synchronize failed");
+}
+int nsb_profile_enable(nsb_handle c, int on) {
+  if (!c) return -1;
+  c->prof.collect(c->stream);
+  c->prof.on = on != 0;
+  return 0;
+}
+int nsb_profile_reset(nsb_handle c) {
+  if (!c) return -1;
+  c->prof.collect(c->stream);
+  c->prof.reset();
+  return 0;
+}
+int nsb_profile_get(nsb_handle c, const char* name, double* total_ms, int64_t* launches) {
+  if (!c) return -1;
+  c->prof.collect(c->stream);
+  for (int i = 0; i < PC_N; ++i)
+    if (std::strcmp(name, kProfNames[i]) == 0) {
+      if (total_ms) *total_ms = c->prof.ms[i];
+      if (launches) *launches = c->prof.cnt[i];
+      return 0;
+    }
+  return fail(c, "unknown profile class");
+}
+int nsb_launch_count(nsb_handle c, int64_t* n) {
+  if (!c) return -1;
+  *n = c->launches;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// Host-side, one-time construction of the node-block sparse structure that every kernel
+// works on (DESIGN.md "Data layout").  Input is exactly what the reference's setup()
+// produces with deal.II (reference src/classes/NavierStokes.cpp:83-104, 256-273): the
+// per-cell global DoF indices in FESystem local order after the component-wise
+// renumbering, n_u, n_p, and the vertex coordinates.  The sparsity pattern is the union
+// of the dense cell couplings (make_sparsity_pattern, keep_constrained_dofs = true),
+// stored compressed at node granularity: the velocity DoFs of one P2 node are
+// consecutive (dim*k .. dim*k+dim-1), so one neighbour-node index stands for dim columns.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace nsb {
+
+struct Structure {
+  int dim = 0, NV = 0, NN = 0, DPC = 0;
+  int rank = 0, nranks = 1;
+  // global sizes
+  int64_t n_u_glob = 0, n_p_glob = 0, n_cells_glob = 0;
+  // local sizes: nodes = P2 nodes (velocity), pids = pressure DoFs (vertices)
+  int nn_own = 0, nn_ghost = 0, np_own = 0, np_ghost = 0, nc = 0;
+  std::vector<int64_t> node_gid;     // [nn_own+nn_ghost] global node id (= global velocity dof / dim)
+  std::vector<int64_t> pid_gid;      // [np_own+np_ghost] global pressure id (= global dof - n_u)
+  std::vector<int> cell_gid;         // [nc] global cell index
+  std::vector<int> cell_nodes;       // [nc][NN] local node ids
+  std::vector<int> cell_pids;        // [nc][NV] local pressure ids
+  std::vector<int> node_pid;         // [nn_tot] local pressure id of a vertex node, -1 for line nodes
+  std::vector<int> pid_node;         // [np_tot] local node id of the vertex carrying this pressure DoF
+  // adjacency of owned nodes, neighbours sorted by global id (=> ascending global column)
+  std::vector<int64_t> nbr_ptr;      // [nn_own+1]
+  std::vector<int> nbr;              // local node ids
+  std::vector<int64_t> pnbr_ptr;     // [nn_own+1]
+  std::vector<int> pnbr;             // local pressure ids
+  std::vector<int> selfrank;         // [nn_own] position of the node in its own nbr list
+  std::vector<int> pselfrank;        // [np_own] position of the pressure id in pnbr of its vertex node
+  std::vector<int64_t> rowbase;      // [nn_own] offset of scalar row (node,0) in the value array
+  std::vector<int64_t> prowbase;     // [np_own] offset of the pressure row
+  int64_t nnz_local = 0;
+  // node -> cells (ascending local cell), packed cell<<4 | local node index
+  std::vector<int64_t> n2c_ptr;      // [nn_own+1]
+  std::vector<uint32_t> n2c;
+  // per cell: position of node b / vertex j in the neighbour lists of node a
+  std::vector<uint16_t> rank_uu;     // [nc][NN][NN]
+  std::vector<uint16_t> rank_up;     // [nc][NN][NV]
+  // per cell geometry (constant in time): grad lambda_k [NV][DIM], |det J|, diameter h; 16 doubles/cell
+  std::vector<double> cell_geom;
+  // halo plan (multi-GPU): ghosts are ordered by (owner rank, global id)
+  std::vector<int> peer;                       // ranks this rank exchanges with
+  std::vector<std::vector<int>> send_nodes;    // per peer: owned local node ids to send
+  std::vector<std::vector<int>> send_pids;     // per peer: owned local pressure ids to send
+  std::vector<int> recv_node_count, recv_pid_count;   // per peer, contiguous in the ghost ranges
+  int max_row_len = 0, max_node_smem_doubles = 0;
+
+  // vector layout: [u_own (dim*nn_own) | p_own | u_ghost | p_ghost]
+  int64_t n_own_dofs() const { return (int64_t)dim * nn_own + np_own; }
+  int64_t n_tot_dofs() const { return (int64_t)dim * (nn_own + nn_ghost) + np_own + np_ghost; }
+  int64_t node_xoff(int A) const {
+    return A < nn_own ? (int64_t)dim * A : n_own_dofs() + (int64_t)dim * (A - nn_own);
+  }
+  int64_t pid_xoff(int P) const {
+    return P < np_own ? (int64_t)dim * nn_own + P
+                      : n_own_dofs() + (int64_t)dim * nn_ghost + (P - np_own);
+  }
+  int row_len(int A) const {
+    return dim * (int)(nbr_ptr[A + 1] - nbr_ptr[A]) + (int)(pnbr_ptr[A + 1] - pnbr_ptr[A]);
+  }
+};
+
+// Builds the structure for `rank` of `nranks`.  cell_part may be null (single rank).
+// Returns an empty string on success, else an error message.
+std::string build_structure(int dim, int64_t n_vertices, const double* coords, int64_t n_cells,
+                            const uint32_t* cell_vertices, const uint32_t* cell_dofs, int64_t n_u,
+                            int64_t n_p, const int32_t* cell_part, int rank, int nranks, Structure& S);
+
+// Expands the local rows to scalar CSR with GLOBAL column indices, rows in local owned
+// order (velocity rows then pressure rows); for the bit-exact pattern check.
+void export_pattern(const Structure& S, std::vector<int64_t>& rowptr, std::vector<uint32_t>& col);
+
+// Global row index (deal.II numbering) of every local owned row, in local order.
+void export_row_gids(const Structure& S, std::vector<int64_t>& gid);
+
+}  // namespace nsb
