@@ -38,8 +38,8 @@ typedef struct nsb_params {
 /* options of the GPU preconditioner that stands in for Ifpack ILU / ML AMG
  * (reference NavierStokes.hpp:302-315).  Zero-initialise for defaults. */
 typedef struct nsb_solver_opts {
-  int32_t cheb_degree_F;    /* block-Jacobi Chebyshev degree on F           (default 3)   */
-  double cheb_ratio_F;      /* lambda_max / lambda_min target               (default 30)  */
+  int32_t poly_degree_F;    /* degree of the GMRES polynomial on Dinv*F      (default 6)   */
+  int32_t poly_refresh;     /* rebuild that polynomial every k-th solve      (default 1)   */
   int32_t cheb_degree_Mp;   /* Jacobi Chebyshev degree on M_p               (default 3)   */
   int32_t amg_smoother_degree; /* Chebyshev sweeps per level, pre and post  (default 2)   */
   double schur_mass_coeff;  /* coefficient of M_p^-1; <0 = theta*nu + gamma_graddiv (default),

@@ -30,7 +30,7 @@ class NsbParams(C.Structure):
 
 
 class NsbSolverOpts(C.Structure):
-    _fields_ = [("cheb_degree_F", C.c_int32), ("cheb_ratio_F", C.c_double), ("cheb_degree_Mp", C.c_int32),
+    _fields_ = [("poly_degree_F", C.c_int32), ("poly_refresh", C.c_int32), ("cheb_degree_Mp", C.c_int32),
                 ("amg_smoother_degree", C.c_int32), ("schur_mass_coeff", C.c_double), ("reorthogonalize", C.c_int32)]
 
 
@@ -135,9 +135,9 @@ class Device:
         p = NsbParams(dt, theta, nu, rho, gamma, int(use_supg), int(first_order_ustar))
         self._ck(lib().nsb_set_params(self.h, C.byref(p)))
 
-    def set_solver_opts(self, cheb_degree_F=0, cheb_ratio_F=0.0, cheb_degree_Mp=0, amg_smoother_degree=0,
+    def set_solver_opts(self, poly_degree_F=0, poly_refresh=0, cheb_degree_Mp=0, amg_smoother_degree=0,
                         schur_mass_coeff=0.0, reorthogonalize=1):
-        o = NsbSolverOpts(cheb_degree_F, cheb_ratio_F, cheb_degree_Mp, amg_smoother_degree, schur_mass_coeff, reorthogonalize)
+        o = NsbSolverOpts(poly_degree_F, poly_refresh, cheb_degree_Mp, amg_smoother_degree, schur_mass_coeff, reorthogonalize)
         self._ck(lib().nsb_set_solver_opts(self.h, C.byref(o)))
 
     def set_vector(self, which, v):

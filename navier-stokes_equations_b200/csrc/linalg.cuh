@@ -55,17 +55,21 @@ k_spmv_full(DevMesh M, const VT* __restrict__ vals, const double* __restrict__ x
 
 // ------------------------------------------------------------------------------------
 // Velocity block F = A(0,0) only (columns < dim*nb of the velocity rows), with the fused
-// epilogues of the block-Jacobi Chebyshev iteration used in place of Ifpack ILU(1)
-// (reference NavierStokes.hpp:302-304, 325):
+// epilogues of the polynomial preconditioner used in place of Ifpack ILU(1)
+// (reference NavierStokes.hpp:302-304, 325).  Dinv = inverse node-diagonal blocks.
 //   MODE 0:  y = F x
-//   MODE 1:  r = r0 - F z ; d = c1 d + c2 Dinv r ; znew = z + d            (one Chebyshev step)
-//   MODE 2:  y = Dinv (F x)                                               (power iteration)
+//   MODE 2:  y = Dinv (F x)                                     (Arnoldi on the scaled block)
+//   MODE 3:  t = Dinv (F x) ; y = cu*u + ct*t ; poly += cpu*u + cpy*y   (one root of the
+//            GMRES polynomial in product form; u is read at the node's own entries)
 // ------------------------------------------------------------------------------------
+struct PolyCoef {
+  double cu, ct, cpu, cpy;
+};
+
 template <int DIM, int MODE, typename VT>
 __global__ void __launch_bounds__(SPMV_WARPS * 32)
 k_spmv_vel(DevMesh M, const VT* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
-           const double* __restrict__ r0v, double* __restrict__ dv, const double* __restrict__ dinv,
-           double c1, double c2) {
+           const double* __restrict__ u, double* __restrict__ poly, const double* __restrict__ dinv, PolyCoef pc) {
   const int lane = threadIdx.x & 31;
   const int A = blockIdx.x * SPMV_WARPS + (threadIdx.x >> 5);
   if (A >= M.nn_own) return;
@@ -92,18 +96,16 @@ k_spmv_vel(DevMesh M, const VT* __restrict__ vals, const double* __restrict__ x,
       for (int c = 1; c < DIM; ++c) if (lane == c) v = sum[c];
       y[row] = v;
     } else {
-      double r[DIM];
-#pragma unroll
-      for (int c = 0; c < DIM; ++c) r[c] = (MODE == 1) ? (r0v[DIM * A + c] - sum[c]) : sum[c];
       double t = 0.0;
 #pragma unroll
-      for (int c = 0; c < DIM; ++c) t += dinv[(size_t)A * DIM * DIM + lane * DIM + c] * r[c];
-      if (MODE == 1) {
-        const double dn = c1 * dv[row] + c2 * t;
-        dv[row] = dn;
-        y[row] = x[row] + dn;
-      } else {
+      for (int c = 0; c < DIM; ++c) t += dinv[(size_t)A * DIM * DIM + lane * DIM + c] * sum[c];
+      if (MODE == 2) {
         y[row] = t;
+      } else {
+        const double uv = u[row];
+        const double yv = pc.cu * uv + pc.ct * t;
+        y[row] = yv;
+        poly[row] += pc.cpu * uv + pc.cpy * yv;
       }
     }
   }
@@ -128,23 +130,20 @@ k_schur_rhs(DevMesh M, const VT* __restrict__ vals, const double* __restrict__ y
   if (lane == 0) t[Pid] = g[DIM * M.nn_own + Pid] - s;
 }
 
-// dv = Dinv r / theta ; z = dv   (first Chebyshev step from z0 = 0), block version
+// y = Dinv x (node-block Jacobi scaling of a velocity vector)
 template <int DIM>
-__global__ void k_cheb_first_vel(int nn, const double* __restrict__ dinv, const double* __restrict__ r0,
-                                 double* __restrict__ dv, double* __restrict__ z, double inv_theta) {
+__global__ void k_block_scale(int nn, const double* __restrict__ dinv, const double* __restrict__ x, double* __restrict__ y) {
   const int A = blockIdx.x * blockDim.x + threadIdx.x;
   if (A >= nn) return;
   double r[DIM];
 #pragma unroll
-  for (int c = 0; c < DIM; ++c) r[c] = r0[DIM * A + c];
+  for (int c = 0; c < DIM; ++c) r[c] = x[DIM * A + c];
 #pragma unroll
   for (int e = 0; e < DIM; ++e) {
     double t = 0.0;
 #pragma unroll
     for (int c = 0; c < DIM; ++c) t += dinv[(size_t)A * DIM * DIM + e * DIM + c] * r[c];
-    t *= inv_theta;
-    dv[DIM * A + e] = t;
-    z[DIM * A + e] = t;
+    y[DIM * A + e] = t;
   }
 }
 

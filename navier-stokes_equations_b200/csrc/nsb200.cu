@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "amg.hpp"
+#include "small_eig.hpp"
 #include "assemble.cuh"
 #include "device.cuh"
 #include "linalg.cuh"
@@ -175,11 +176,11 @@ struct nsb_ctx {
   DBuf<double> coarse_inv;
   int coarse_n = 0;
   // preconditioner / Krylov workspace
-  DBuf<double> w_z0, w_z1, w_d, w_t, w_y1, w_m0, w_m1, w_md, w_in, w_tmp, w_pin;
+  DBuf<double> w_z0, w_z1, w_d, w_t, w_y1, w_m0, w_m1, w_md, w_in, w_tmp, w_pin, w_poly;
+  std::vector<std::pair<double, double>> poly_roots;   // harmonic Ritz values (re, im>=0), Leja ordered
   DBuf<double> V;                   // Krylov basis, (m+1) vectors of n_own
   int V_cap = 0;
   DBuf<double> partial, d_h, d_nrm;
-  double F_lmax = 0.0;
   DBuf<double> eigv;                // power-iteration vector for lambda_max(Dinv F)
   bool eig_init = false;
   int solves = 0;
@@ -297,13 +298,19 @@ void spmv_full(nsb_ctx* c, const double* x, double* y) {
 }
 
 template <int MODE>
-void spmv_vel(nsb_ctx* c, const double* x, double* y, const double* r0, double* d, double c1, double c2) {
+void spmv_vel(nsb_ctx* c, const double* x, double* y, const double* u, double* poly, PolyCoef pc) {
   size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
   const int g = nblk(c->S.nn_own, SPMV_WARPS);
-  if (c->dim == 2) k_spmv_vel<2, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, x, y, r0, d, c->dinv.p, c1, c2);
-  else k_spmv_vel<3, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, x, y, r0, d, c->dinv.p, c1, c2);
+  if (c->dim == 2) k_spmv_vel<2, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, x, y, u, poly, c->dinv.p, pc);
+  else k_spmv_vel<3, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, x, y, u, poly, c->dinv.p, pc);
   c->launch_check();
   c->prof.end(id, c->stream);
+}
+
+void block_scale(nsb_ctx* c, const double* x, double* y) {
+  if (c->dim == 2) k_block_scale<2><<<nblk(c->S.nn_own, 256), 256, 0, c->stream>>>(c->S.nn_own, c->dinv.p, x, y);
+  else k_block_scale<3><<<nblk(c->S.nn_own, 256), 256, 0, c->stream>>>(c->S.nn_own, c->dinv.p, x, y);
+  c->launch_check();
 }
 
 double device_norm2(nsb_ctx* c, const double* x, long long n) {
@@ -335,31 +342,163 @@ struct Cheb {
   }
 };
 
-// lambda_max(Dinv F) by power iteration (block-Jacobi scaled velocity block)
-void estimate_F_lmax(nsb_ctx* c, int iters) {
-  const long long nu = (long long)c->dim * c->S.nn_own;
+// ---- GMRES polynomial for the velocity block ---------------------------------------------
+// p(B) ~ B^-1 with B = Dinv F (node-block-Jacobi scaled), p of degree d-1 defined by the
+// harmonic Ritz values theta_i of d Arnoldi steps from a fixed pseudo-random vector
+// (Loe & Morgan's polynomial preconditioned GMRES).  p is a FIXED linear operator between
+// rebuilds, so the outer iteration stays plain (non-flexible) left-preconditioned GMRES like
+// the reference's.  Robust for the convection-dominated (complex) spectrum where Chebyshev
+// on a real interval diverges.
+
+void setup_F_poly(nsb_ctx* c) {
+  const Structure& S = c->S;
+  const long long nu = (long long)c->dim * S.nn_own;
+  const long long n = S.n_own_dofs();
+  int d = std::max(1, std::min(c->opt.poly_degree_F, 24));
+  if (c->V_cap < d + 1) { c->V.alloc((size_t)(std::max(d + 1, c->V_cap)) * n); c->V_cap = std::max(d + 1, c->V_cap); }
+  const int nb = nblk(nu, RED_CHUNK);
+  if (c->partial.n < (size_t)nb * (d + 2)) c->partial.alloc((size_t)nb * (d + 2));
+  if (c->d_h.n < (size_t)2 * (d + 2)) c->d_h.alloc(2 * (d + 2));
   if (!c->eig_init) {
-    std::vector<double> h(c->S.n_tot_dofs(), 0.0);
+    std::vector<double> h(nu);
     uint64_t s = 0x2545F4914F6CDD1Dull;
     for (long long i = 0; i < nu; ++i) {
       s ^= s << 13; s ^= s >> 7; s ^= s << 17;
       h[i] = (double)(s >> 11) / 9007199254740992.0 - 0.5;
     }
     c->eigv.upload(h, c->stream);
+    CK(cudaStreamSynchronize(c->stream));
     c->eig_init = true;
   }
-  double lam = c->F_lmax;
-  for (int it = 0; it < iters; ++it) {
-    const double nv = device_norm2(c, c->eigv.p, nu);
-    if (!(nv > 0)) break;
-    k_axpby<<<nblk(nu, 256), 256, 0, c->stream>>>(nu, 0.0, c->eigv.p, 1.0 / nv, c->eigv.p);
+  std::vector<double> H((size_t)(d + 1) * d, 0.0), hh(2 * (d + 2));
+  double beta = device_norm2(c, c->eigv.p, nu);
+  k_axpby<<<nblk(nu, 256), 256, 0, c->stream>>>(nu, 1.0 / beta, c->eigv.p, 0.0, c->V.p);
+  c->launch_check();
+  int dd = d;
+  for (int k = 0; k < d; ++k) {
+    double* vk = c->V.p + (size_t)k * n;
+    double* w = c->V.p + (size_t)(k + 1) * n;
+    const double* xin = vk;
+    if (c->nranks > 1) {
+      CK(cudaMemcpyAsync(c->w_pin.p, vk, nu * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      halo_exchange(c, c->w_pin.p);
+      xin = c->w_pin.p;
+    }
+    spmv_vel<2>(c, xin, w, nullptr, nullptr, PolyCoef{});
+    for (int pass = 0; pass < 2; ++pass) {
+      k_multi_dot<<<nb, RED_THREADS, 0, c->stream>>>(k + 1, c->V.p, n, w, nu, c->partial.p);
+      c->launch_check();
+      double* hp = c->d_h.p + pass * (d + 2);
+      k_reduce_partials<<<k + 1, RED_THREADS, 0, c->stream>>>(nb, c->partial.p, hp, 0);
+      c->launch_check();
+      allreduce_sum(c, hp, k + 1);
+      k_multi_axpy<<<nb, RED_THREADS, 0, c->stream>>>(k + 1, c->V.p, n, hp, -1.0, w, nu, pass == 1 ? c->partial.p : nullptr);
+      c->launch_check();
+    }
+    k_reduce_partials<<<1, RED_THREADS, 0, c->stream>>>(nb, c->partial.p, c->d_nrm.p, 0);
     c->launch_check();
-    halo_exchange(c, c->eigv.p);
-    spmv_vel<2>(c, c->eigv.p, c->w_tmp.p, nullptr, nullptr, 0, 0);
-    lam = device_norm2(c, c->w_tmp.p, nu);
-    CK(cudaMemcpyAsync(c->eigv.p, c->w_tmp.p, nu * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    allreduce_sum(c, c->d_nrm.p, 1);
+    k_scale_by_inv_norm<<<nblk(nu, 256), 256, 0, c->stream>>>(nu, w, c->d_nrm.p, w);
+    c->launch_check();
+    double nrm2 = 0;
+    CK(cudaMemcpyAsync(hh.data(), c->d_h.p, sizeof(double) * 2 * (d + 2), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&nrm2, c->d_nrm.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i <= k; ++i) H[(size_t)i * d + k] = hh[i] + hh[(d + 2) + i];
+    H[(size_t)(k + 1) * d + k] = std::sqrt(nrm2);
+    if (!(nrm2 > 1e-28)) { dd = k + 1; break; }
   }
-  c->F_lmax = lam;
+  // harmonic Ritz values: eig(Hd + h_{d+1,d}^2 f e_d^T),  Hd^T f = e_d
+  d = dd;
+  std::vector<double> Hd((size_t)d * d), At((size_t)d * d), f(d, 0.0);
+  const int ldh = std::max(1, std::min(c->opt.poly_degree_F, 24));
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) { Hd[(size_t)i * d + j] = H[(size_t)i * ldh + j]; At[(size_t)j * d + i] = H[(size_t)i * ldh + j]; }
+  f[d - 1] = 1.0;
+  {  // Gaussian elimination with partial pivoting on At f = e_d
+    std::vector<int> piv(d);
+    for (int col = 0; col < d; ++col) {
+      int p = col;
+      for (int r = col + 1; r < d; ++r) if (std::fabs(At[(size_t)r * d + col]) > std::fabs(At[(size_t)p * d + col])) p = r;
+      if (p != col) { for (int k = 0; k < d; ++k) std::swap(At[(size_t)col * d + k], At[(size_t)p * d + k]); std::swap(f[col], f[p]); }
+      const double dg = At[(size_t)col * d + col];
+      for (int r = col + 1; r < d; ++r) {
+        const double m = At[(size_t)r * d + col] / dg;
+        if (m == 0.0) continue;
+        for (int k = col; k < d; ++k) At[(size_t)r * d + k] -= m * At[(size_t)col * d + k];
+        f[r] -= m * f[col];
+      }
+    }
+    for (int r = d - 1; r >= 0; --r) {
+      double s = f[r];
+      for (int k = r + 1; k < d; ++k) s -= At[(size_t)r * d + k] * f[k];
+      f[r] = s / At[(size_t)r * d + r];
+    }
+  }
+  const double hl = H[(size_t)d * ldh + (d - 1)];
+  for (int i = 0; i < d; ++i) Hd[(size_t)i * d + (d - 1)] += hl * hl * f[i];
+  std::vector<double> wr, wi;
+  if (!hessenberg_eigs(d, Hd, wr, wi)) throw CudaErr{"harmonic Ritz eigenvalue iteration did not converge"};
+  // Leja ordering, complex conjugates kept adjacent (positive imaginary part first)
+  std::vector<std::pair<double, double>> th, out;
+  for (int i = 0; i < d; ++i) if (wi[i] >= 0) th.emplace_back(wr[i], wi[i]);
+  auto mag = [](const std::pair<double, double>& z) { return std::hypot(z.first, z.second); };
+  while (!th.empty()) {
+    size_t best = 0;
+    double bv = -1e300;
+    for (size_t i = 0; i < th.size(); ++i) {
+      double v;
+      if (out.empty()) v = mag(th[i]);
+      else {
+        v = 0;
+        for (auto& o : out) {
+          v += std::log(std::hypot(th[i].first - o.first, th[i].second - o.second) + 1e-300);
+          if (o.second != 0) v += std::log(std::hypot(th[i].first - o.first, th[i].second + o.second) + 1e-300);
+        }
+      }
+      if (v > bv) { bv = v; best = i; }
+    }
+    out.push_back(th[best]);
+    th.erase(th.begin() + best);
+  }
+  c->poly_roots = out;
+}
+
+// y_u = p(B) Dinv x_u  ~ F^-1 x_u ; result left in c->w_poly
+void apply_F_poly(nsb_ctx* c, const double* x) {
+  const long long nu = (long long)c->dim * c->S.nn_own;
+  double* prod = c->w_z0.p;
+  double* other = c->w_z1.p;
+  double* tmp = c->w_d.p;
+  double* poly = c->w_poly.p;
+  block_scale(c, x, prod);
+  CK(cudaMemsetAsync(poly, 0, nu * sizeof(double), c->stream));
+  const auto& R = c->poly_roots;
+  for (size_t k = 0; k < R.size(); ++k) {
+    const bool last = (k + 1 == R.size());
+    const double a = R[k].first, b = R[k].second;
+    if (b == 0.0) {
+      if (last) {
+        k_axpby<<<nblk(nu, 256), 256, 0, c->stream>>>(nu, 1.0 / a, prod, 1.0, poly);
+        c->launch_check();
+      } else {
+        // poly += prod/theta ; prod <- prod - B prod / theta
+        halo_exchange(c, prod);
+        spmv_vel<3>(c, prod, other, prod, poly, PolyCoef{1.0, -1.0 / a, 1.0 / a, 0.0});
+        std::swap(prod, other);
+      }
+    } else {
+      const double m2 = a * a + b * b;
+      // tmp = 2a prod - B prod ; poly += tmp/m2 ; prod <- prod - B tmp / m2
+      halo_exchange(c, prod);
+      spmv_vel<3>(c, prod, tmp, prod, poly, PolyCoef{2.0 * a, -1.0, 0.0, 1.0 / m2});
+      if (!last) {
+        halo_exchange(c, tmp);
+        spmv_vel<3>(c, tmp, other, prod, poly, PolyCoef{1.0, -1.0 / m2, 0.0, 0.0});
+        std::swap(prod, other);
+      }
+    }
+  }
 }
 
 // ---- pressure-space pieces (global, replicated vectors of length n_p) -------------------
@@ -424,21 +563,9 @@ void precond_apply(nsb_ctx* c, const double* x, double* y) {
   const Structure& S = c->S;
   const int dim = c->dim;
   const long long nu = (long long)dim * S.nn_own;
-  // --- step 1: block-Jacobi Chebyshev on F
-  const int deg = c->opt.cheb_degree_F;
-  Cheb ch(1.1 * c->F_lmax, 1.1 * c->F_lmax / c->opt.cheb_ratio_F);
-  double* z = c->w_z0.p;
-  double* zo = c->w_z1.p;
-  if (dim == 2) k_cheb_first_vel<2><<<nblk(S.nn_own, 256), 256, 0, c->stream>>>(S.nn_own, c->dinv.p, x, c->w_d.p, z, 1.0 / ch.theta);
-  else k_cheb_first_vel<3><<<nblk(S.nn_own, 256), 256, 0, c->stream>>>(S.nn_own, c->dinv.p, x, c->w_d.p, z, 1.0 / ch.theta);
-  c->launch_check();
-  for (int k = 1; k < deg; ++k) {
-    double c1, c2;
-    ch.next(c1, c2);
-    halo_exchange(c, z);
-    spmv_vel<1>(c, z, zo, x, c->w_d.p, c1, c2);
-    std::swap(z, zo);
-  }
+  // --- step 1: y0 = p(Dinv F) Dinv x0
+  apply_F_poly(c, x);
+  double* z = c->w_poly.p;
   CK(cudaMemcpyAsync(y, z, nu * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   // --- step 2: t = x1 - B y0
   halo_exchange(c, z);
@@ -720,7 +847,7 @@ int nsb_create(int dim, int device, nsb_handle* out) {
   fill_tables(3, T3);
   CK(cudaMemcpyToSymbol(c_fe2, &T2, sizeof(FeTables)));
   CK(cudaMemcpyToSymbol(c_fe3, &T3, sizeof(FeTables)));
-  c->opt.cheb_degree_F = 3; c->opt.cheb_ratio_F = 30.0; c->opt.cheb_degree_Mp = 3;
+  c->opt.poly_degree_F = 6; c->opt.poly_refresh = 1; c->opt.cheb_degree_Mp = 3;
   c->opt.amg_smoother_degree = 2; c->opt.schur_mass_coeff = -1.0; c->opt.reorthogonalize = 1;
   c->par.dt = 0.01; c->par.theta = 1.0; c->par.nu = 1e-3; c->par.rho = 1.0; c->par.gamma = 0.1;
   c->d_nrm.alloc(4);
@@ -830,7 +957,7 @@ int nsb_upload_mesh(nsb_handle c, int64_t n_vertices, const double* coords, int6
   // vectors and system storage
   const size_t nt = (size_t)S.n_tot_dofs();
   for (DBuf<double>* v : {&c->v_old, &c->v_oldold, &c->v_cur, &c->v_sol, &c->v_rhs, &c->cval, &c->w_z0, &c->w_z1, &c->w_d,
-                          &c->w_in, &c->w_tmp, &c->w_pin}) {
+                          &c->w_in, &c->w_tmp, &c->w_pin, &c->w_poly}) {
     v->alloc(nt);
     v->zero(st);
   }
@@ -842,7 +969,7 @@ int nsb_upload_mesh(nsb_handle c, int64_t n_vertices, const double* coords, int6
   c->partial.alloc((size_t)nblk(S.n_own_dofs(), RED_CHUNK) * 4);
   CK(cudaStreamSynchronize(st));
   c->have_mesh = true; c->have_matrix = false; c->have_pressure = false;
-  c->eig_init = false; c->F_lmax = 0; c->solves = 0; c->V_cap = 0;
+  c->eig_init = false; c->poly_roots.clear(); c->solves = 0; c->V_cap = 0;
   return 0;
   NSB_CATCH(c)
 }
@@ -917,8 +1044,8 @@ int nsb_set_params(nsb_handle c, const nsb_params* p) {
 int nsb_set_solver_opts(nsb_handle c, const nsb_solver_opts* o) {
   if (!c || !o) return -1;
   nsb_solver_opts n = *o;
-  if (n.cheb_degree_F <= 0) n.cheb_degree_F = 3;
-  if (!(n.cheb_ratio_F > 1)) n.cheb_ratio_F = 30.0;
+  if (n.poly_degree_F <= 0) n.poly_degree_F = 6;
+  if (n.poly_refresh <= 0) n.poly_refresh = 1;
   if (n.cheb_degree_Mp <= 0) n.cheb_degree_Mp = 3;
   if (n.amg_smoother_degree <= 0) n.amg_smoother_degree = 2;
   if (n.schur_mass_coeff == 0.0) n.schur_mass_coeff = -1.0;
@@ -1081,8 +1208,7 @@ int nsb_solve(nsb_handle c, int max_it, double tol_rel, int n_tmp, int* iteratio
   CK(cudaSetDevice(c->device));
   int it = 0;
   double res = 0;
-  // eigenvalue bound of the block-Jacobi scaled velocity block: full estimate once, cheap refresh after
-  estimate_F_lmax(c, c->solves == 0 ? 20 : 2);
+  if (c->poly_roots.empty() || c->solves % c->opt.poly_refresh == 0) setup_F_poly(c);
   const double bnorm = device_norm2(c, c->v_rhs.p, c->S.n_own_dofs());
   const int rc = gmres(c, max_it, tol_rel * bnorm, n_tmp > 2 ? n_tmp : 150, &it, &res);
   // constraints.distribute(x)   (cpp:566, 862)
@@ -1185,6 +1311,15 @@ int nsb_profile_get(nsb_handle c, const char* name, double* total_ms, int64_t* l
     }
   return fail(c, "unknown profile class");
 }
+/* host-only helper exported for the CPU test-suite: eigenvalues of an upper-Hessenberg matrix */
+int nsb_test_hessenberg_eigs(int n, const double* a, double* wr, double* wi) {
+  std::vector<double> A(a, a + (size_t)n * n), r, i;
+  if (!hessenberg_eigs(n, A, r, i)) return 1;
+  std::copy(r.begin(), r.end(), wr);
+  std::copy(i.begin(), i.end(), wi);
+  return 0;
+}
+
 int nsb_launch_count(nsb_handle c, int64_t* n) {
   if (!c) return -1;
   *n = c->launches;
