@@ -38,8 +38,10 @@ typedef struct nsb_params {
 /* options of the GPU preconditioner that stands in for Ifpack ILU / ML AMG
  * (reference NavierStokes.hpp:302-315).  Zero-initialise for defaults. */
 typedef struct nsb_solver_opts {
-  int32_t poly_degree_F;    /* degree of the GMRES polynomial on Dinv*F      (default 6)   */
+  int32_t poly_degree_F;    /* max degree of the GMRES polynomial on Dinv*F  (default 32)  */
   int32_t poly_refresh;     /* rebuild that polynomial every k-th solve      (default 1)   */
+  double poly_target;       /* stop growing the degree once the polynomial reduces the probe
+                               vector's residual below this                  (default 0.12) */
   int32_t cheb_degree_Mp;   /* Jacobi Chebyshev degree on M_p               (default 3)   */
   int32_t amg_smoother_degree; /* Chebyshev sweeps per level, pre and post  (default 2)   */
   double schur_mass_coeff;  /* coefficient of M_p^-1; <0 = theta*nu + gamma_graddiv (default),
@@ -133,6 +135,9 @@ int nsb_synchronize(nsb_handle h);
 int nsb_profile_enable(nsb_handle h, int on);
 int nsb_profile_reset(nsb_handle h);
 int nsb_profile_get(nsb_handle h, const char* name, double* total_ms, int64_t* launches);
+/* what the last solve used: degree of the velocity polynomial, its residual reduction on the
+ * probe vector, number of multigrid levels of K_p */
+int nsb_solver_info(nsb_handle h, int* poly_degree, double* poly_probe_residual, int* amg_levels);
 /* how many kernels this library launched since nsb_create */
 int nsb_launch_count(nsb_handle h, int64_t* n);
 

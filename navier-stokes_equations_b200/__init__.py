@@ -30,7 +30,7 @@ class NsbParams(C.Structure):
 
 
 class NsbSolverOpts(C.Structure):
-    _fields_ = [("poly_degree_F", C.c_int32), ("poly_refresh", C.c_int32), ("cheb_degree_Mp", C.c_int32),
+    _fields_ = [("poly_degree_F", C.c_int32), ("poly_refresh", C.c_int32), ("poly_target", C.c_double), ("cheb_degree_Mp", C.c_int32),
                 ("amg_smoother_degree", C.c_int32), ("schur_mass_coeff", C.c_double), ("reorthogonalize", C.c_int32)]
 
 
@@ -135,9 +135,9 @@ class Device:
         p = NsbParams(dt, theta, nu, rho, gamma, int(use_supg), int(first_order_ustar))
         self._ck(lib().nsb_set_params(self.h, C.byref(p)))
 
-    def set_solver_opts(self, poly_degree_F=0, poly_refresh=0, cheb_degree_Mp=0, amg_smoother_degree=0,
+    def set_solver_opts(self, poly_degree_F=0, poly_refresh=0, poly_target=0.0, cheb_degree_Mp=0, amg_smoother_degree=0,
                         schur_mass_coeff=0.0, reorthogonalize=1):
-        o = NsbSolverOpts(poly_degree_F, poly_refresh, cheb_degree_Mp, amg_smoother_degree, schur_mass_coeff, reorthogonalize)
+        o = NsbSolverOpts(poly_degree_F, poly_refresh, poly_target, cheb_degree_Mp, amg_smoother_degree, schur_mass_coeff, reorthogonalize)
         self._ck(lib().nsb_set_solver_opts(self.h, C.byref(o)))
 
     def set_vector(self, which, v):
@@ -223,6 +223,11 @@ class Device:
             self._ck(lib().nsb_profile_get(self.h, name.encode(), C.byref(ms), C.byref(n)))
             out[name] = (ms.value, n.value)
         return out
+
+    def solver_info(self):
+        d, r, l = C.c_int(), C.c_double(), C.c_int()
+        self._ck(lib().nsb_solver_info(self.h, C.byref(d), C.byref(r), C.byref(l)))
+        return dict(poly_degree=d.value, poly_probe_residual=r.value, amg_levels=l.value)
 
     def launch_count(self):
         n = C.c_int64()

@@ -177,6 +177,7 @@ struct nsb_ctx {
   int coarse_n = 0;
   // preconditioner / Krylov workspace
   DBuf<double> w_z0, w_z1, w_d, w_t, w_y1, w_m0, w_m1, w_md, w_in, w_tmp, w_pin, w_poly;
+  double poly_probe_res = 1.0;
   std::vector<std::pair<double, double>> poly_roots;   // harmonic Ritz values (re, im>=0), Leja ordered
   DBuf<double> V;                   // Krylov basis, (m+1) vectors of n_own
   int V_cap = 0;
@@ -354,7 +355,7 @@ void setup_F_poly(nsb_ctx* c) {
   const Structure& S = c->S;
   const long long nu = (long long)c->dim * S.nn_own;
   const long long n = S.n_own_dofs();
-  int d = std::max(1, std::min(c->opt.poly_degree_F, 24));
+  int d = std::max(1, std::min(c->opt.poly_degree_F, 64));
   if (c->V_cap < d + 1) { c->V.alloc((size_t)(std::max(d + 1, c->V_cap)) * n); c->V_cap = std::max(d + 1, c->V_cap); }
   const int nb = nblk(nu, RED_CHUNK);
   if (c->partial.n < (size_t)nb * (d + 2)) c->partial.alloc((size_t)nb * (d + 2));
@@ -370,7 +371,8 @@ void setup_F_poly(nsb_ctx* c) {
     CK(cudaStreamSynchronize(c->stream));
     c->eig_init = true;
   }
-  std::vector<double> H((size_t)(d + 1) * d, 0.0), hh(2 * (d + 2));
+  std::vector<double> H((size_t)(d + 1) * d, 0.0), hh(2 * (d + 2)), gcs(d + 1), gsn(d + 1);
+  double gres = 1.0;
   double beta = device_norm2(c, c->eigv.p, nu);
   k_axpby<<<nblk(nu, 256), 256, 0, c->stream>>>(nu, 1.0 / beta, c->eigv.p, 0.0, c->V.p);
   c->launch_check();
@@ -407,11 +409,26 @@ void setup_F_poly(nsb_ctx* c) {
     for (int i = 0; i <= k; ++i) H[(size_t)i * d + k] = hh[i] + hh[(d + 2) + i];
     H[(size_t)(k + 1) * d + k] = std::sqrt(nrm2);
     if (!(nrm2 > 1e-28)) { dd = k + 1; break; }
+    // GMRES residual of the probe vector after k+1 steps (Givens on a copy of column k)
+    {
+      std::vector<double> col(k + 2);
+      for (int i = 0; i <= k + 1; ++i) col[i] = H[(size_t)i * d + k];
+      for (int i = 0; i < k; ++i) {
+        const double t = gcs[i] * col[i] + gsn[i] * col[i + 1];
+        col[i + 1] = -gsn[i] * col[i] + gcs[i] * col[i + 1];
+        col[i] = t;
+      }
+      const double r = std::hypot(col[k], col[k + 1]);
+      gcs[k] = col[k] / r; gsn[k] = col[k + 1] / r;
+      gres *= std::fabs(gsn[k]);
+      if (gres <= c->opt.poly_target && k + 1 >= 2) { dd = k + 1; break; }
+    }
   }
+  c->poly_probe_res = gres;
   // harmonic Ritz values: eig(Hd + h_{d+1,d}^2 f e_d^T),  Hd^T f = e_d
   d = dd;
   std::vector<double> Hd((size_t)d * d), At((size_t)d * d), f(d, 0.0);
-  const int ldh = std::max(1, std::min(c->opt.poly_degree_F, 24));
+  const int ldh = std::max(1, std::min(c->opt.poly_degree_F, 64));
   for (int i = 0; i < d; ++i)
     for (int j = 0; j < d; ++j) { Hd[(size_t)i * d + j] = H[(size_t)i * ldh + j]; At[(size_t)j * d + i] = H[(size_t)i * ldh + j]; }
   f[d - 1] = 1.0;
@@ -847,7 +864,7 @@ int nsb_create(int dim, int device, nsb_handle* out) {
   fill_tables(3, T3);
   CK(cudaMemcpyToSymbol(c_fe2, &T2, sizeof(FeTables)));
   CK(cudaMemcpyToSymbol(c_fe3, &T3, sizeof(FeTables)));
-  c->opt.poly_degree_F = 6; c->opt.poly_refresh = 1; c->opt.cheb_degree_Mp = 3;
+  c->opt.poly_degree_F = 32; c->opt.poly_refresh = 1; c->opt.poly_target = 0.12; c->opt.cheb_degree_Mp = 3;
   c->opt.amg_smoother_degree = 2; c->opt.schur_mass_coeff = -1.0; c->opt.reorthogonalize = 1;
   c->par.dt = 0.01; c->par.theta = 1.0; c->par.nu = 1e-3; c->par.rho = 1.0; c->par.gamma = 0.1;
   c->d_nrm.alloc(4);
@@ -1044,7 +1061,8 @@ int nsb_set_params(nsb_handle c, const nsb_params* p) {
 int nsb_set_solver_opts(nsb_handle c, const nsb_solver_opts* o) {
   if (!c || !o) return -1;
   nsb_solver_opts n = *o;
-  if (n.poly_degree_F <= 0) n.poly_degree_F = 6;
+  if (n.poly_degree_F <= 0) n.poly_degree_F = 32;
+  if (!(n.poly_target > 0)) n.poly_target = 0.12;
   if (n.poly_refresh <= 0) n.poly_refresh = 1;
   if (n.cheb_degree_Mp <= 0) n.cheb_degree_Mp = 3;
   if (n.amg_smoother_degree <= 0) n.amg_smoother_degree = 2;
@@ -1317,6 +1335,18 @@ int nsb_test_hessenberg_eigs(int n, const double* a, double* wr, double* wi) {
   if (!hessenberg_eigs(n, A, r, i)) return 1;
   std::copy(r.begin(), r.end(), wr);
   std::copy(i.begin(), i.end(), wi);
+  return 0;
+}
+
+int nsb_solver_info(nsb_handle c, int* poly_degree, double* poly_probe_residual, int* amg_levels) {
+  if (!c) return -1;
+  if (poly_degree) {
+    int d = 0;
+    for (auto& r : c->poly_roots) d += (r.second != 0.0) ? 2 : 1;
+    *poly_degree = d;
+  }
+  if (poly_probe_residual) *poly_probe_residual = c->poly_probe_res;
+  if (amg_levels) *amg_levels = (int)c->amg.size();
   return 0;
 }
 

@@ -1,0 +1,82 @@
+"""Developer harness: first-order performance numbers of the CUDA path at scale.
+Usage: python -m tools.gpu_scale LEVEL [steps]      (LEVEL in 5,10,20)"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import dofs as odofs, postprocess as pp  # noqa: E402
+from tools import meshgen  # noqa: E402
+from tools.gpu_check import load_nsb  # noqa: E402
+
+
+def main():
+    level = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    nsb = load_nsb()
+    t0 = time.time()
+    mesh = meshgen.mesh_3d(level)
+    print(f"mesh-3D-{level}: cells {mesh.n_cells} vertices {mesh.n_vertices}  gen {time.time()-t0:.1f}s", flush=True)
+    t0 = time.time()
+    dm = odofs.enumerate_dofs(mesh)
+    print(f"dofs {dm.n_u}+{dm.n_p}  enumerate {time.time()-t0:.1f}s", flush=True)
+    N = dm.n_dofs
+    tc = pp.TEST_CASES["3D-2Z"]
+    dev = nsb.Device(3)
+    t0 = time.time()
+    dev.upload_mesh(mesh.points, mesh.cells, dm.cell_dofs, dm.n_u, dm.n_p)
+    nrows, nnz, nc = dev.sizes()
+    print(f"upload_mesh {time.time()-t0:.1f}s  rows {nrows} nnz {nnz} ({nnz/nrows:.1f}/row)", flush=True)
+    ids = pp.boundary_ids(3)
+    nu = pp.viscosity(3, tc["U_m"], tc["Re"])
+    inlet = pp.inlet_profile(3, tc["U_m"], tc["time_dep"], tc["T_ramp"], 1.0)
+    t0 = time.time()
+    con = odofs.build_constraints(mesh, dm, inlet, ids)
+    cd = con.dofs
+    dev.set_constraints(cd, con.val[cd])
+    print(f"constraints {cd.size} {time.time()-t0:.1f}s", flush=True)
+    full = pp.inlet_profile(3, tc["U_m"], False, 0.0, 0.0)
+    base = np.zeros(N)
+    base[:dm.n_u] = full(dm.support_points[:dm.n_u], dm.component[:dm.n_u])
+    un = base * (1 + 0.1 * np.random.default_rng(1234).uniform(-1, 1, N))
+    unm1 = base * (1 + 0.1 * np.random.default_rng(1235).uniform(-1, 1, N))
+    dev.set_params(0.01, 0.5, nu, 1.0, 0.1, True, False)
+    dev.set_vector(nsb.NSB_SOLUTION_OLD, un)
+    dev.set_vector(nsb.NSB_SOLUTION_OLD_OLD, unm1)
+    dev.assemble_linearized()
+    dev.synchronize()
+    t0 = time.time()
+    dev.assemble_pressure_matrices()
+    print(f"pressure matrices + AMG {time.time()-t0:.1f}s", flush=True)
+    asm_bytes = 8 * nnz + 8 * nrows + 8 * 3 * 4 * nc + 20 * 34 * nc
+    spmv_bytes = 12 * nnz + 16 * nrows + 4 * (nrows + 1)
+    for deg in (0.12, 0.2, 0.08):
+        dev.set_solver_opts(poly_target=deg)
+        dev.profile_enable(True)
+        dev.profile_reset()
+        for s in range(steps):
+            dev.timer_start()
+            dev.assemble_linearized()
+            ta = dev.timer_stop()
+            dev.timer_start()
+            ok, it, res = dev.solve(200, 1e-2, 150)
+            ts = dev.timer_stop()
+            print(f"target {deg} step {s}: assemble {ta:.2f} ms  solve {ts:.1f} ms  iters {it} ok {ok} res {res:.2e} {dev.solver_info()}", flush=True)
+        prof = dev.profile()
+        for k, (ms, n) in prof.items():
+            if n:
+                extra = ""
+                if k == "spmv":
+                    extra = f"  -> {spmv_bytes / (ms / n * 1e-3) / 1e9:.0f} GB/s algorithmic"
+                if k == "asm_rows":
+                    extra = f"  -> {asm_bytes / (ms / n * 1e-3) / 1e9:.0f} GB/s algorithmic (whole assembly bytes)"
+                print(f"   {k:12s} {ms:10.2f} ms / {n:6d} launches = {ms/n:8.3f} ms{extra}")
+        dev.profile_enable(False)
+    dev.close()
+
+
+if __name__ == "__main__":
+    main()
