@@ -233,3 +233,95 @@ class Device:
         n = C.c_int64()
         self._ck(lib().nsb_launch_count(self.h, C.byref(n)))
         return n.value
+
+
+# ------------------------------------------------------------------------------------------------
+# libnsbhost.so: the C++ mirror of the reference's NavierStokes<dim> class (include/nsb200_host.h)
+# ------------------------------------------------------------------------------------------------
+HOST_LIB_PATH = os.path.join(_HERE, "libnsbhost.so")
+_hostlib = None
+
+
+class NshOptions(C.Structure):
+    _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("nccl_unique_id", C.c_void_p),
+                ("write_vtu", C.c_int32), ("verbose", C.c_int32), ("gmres_tolerance", C.c_double), ("deltat", C.c_double),
+                ("max_steps", C.c_int32), ("output_dir", C.c_char_p), ("solver", NsbSolverOpts)]
+
+
+class NshStepInfo(C.Structure):
+    _fields_ = [("time", C.c_double), ("cd", C.c_double), ("cl", C.c_double), ("dp", C.c_double), ("wall_seconds", C.c_double),
+                ("gmres_iterations", C.c_int32), ("newton_iterations", C.c_int32), ("solves", C.c_int32), ("converged", C.c_int32)]
+
+
+def hostlib():
+    global _hostlib
+    if _hostlib is None:
+        lib()
+        if not os.path.exists(HOST_LIB_PATH):
+            raise NsbError("libnsbhost.so is not built")
+        _hostlib = C.CDLL(HOST_LIB_PATH)
+        _hostlib.nsh_last_error.restype = C.c_char_p
+        _hostlib.nsh_device.restype = C.c_void_p
+    return _hostlib
+
+
+class _BorrowedDevice(Device):
+    """View of the nsb_handle owned by a HostSolver (never destroyed from Python)."""
+
+    def __init__(self, handle, dim, n_dofs):
+        self.h = C.c_void_p(handle)
+        self.dim = dim
+        self.n_dofs = n_dofs
+
+    def close(self):
+        self.h = None
+
+
+class HostSolver:
+    """NavierStokes<dim>(TestCases::make_<case>(mesh_file)) driven through the C facade."""
+
+    def __init__(self, case, mesh_file, device=0, rank=0, nranks=1, nccl_unique_id=None, write_vtu=False, verbose=False,
+                 gmres_tolerance=0.0, deltat=0.0, output_dir=None, solver_opts=None):
+        L = hostlib()
+        self._uid = C.create_string_buffer(nccl_unique_id, 128) if nccl_unique_id else None
+        self._outdir = output_dir.encode() if output_dir else None
+        o = NshOptions(device, rank, nranks, C.cast(self._uid, C.c_void_p) if self._uid else None, int(write_vtu),
+                       int(verbose), gmres_tolerance, deltat, -1, self._outdir, solver_opts or NsbSolverOpts())
+        self.h = C.c_void_p()
+        if L.nsh_create(case.encode(), mesh_file.encode(), C.byref(o), C.byref(self.h)) != 0:
+            raise NsbError(L.nsh_last_error().decode())
+        self.dim = 2 if case.startswith("2D") else 3
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise NsbError(hostlib().nsh_last_error().decode())
+
+    def initialize(self):
+        self._ck(hostlib().nsh_initialize(self.h))
+        v = [C.c_int64() for _ in range(4)]
+        self._ck(hostlib().nsh_get_sizes(self.h, *[C.byref(x) for x in v]))
+        self.n_u, self.n_p, self.n_cells, self.n_vertices = [x.value for x in v]
+
+    def step(self):
+        info = NshStepInfo()
+        self._ck(hostlib().nsh_step(self.h, C.byref(info)))
+        return {k: getattr(info, k) for k, _ in NshStepInfo._fields_}
+
+    def solution(self):
+        out = np.empty(self.n_u + self.n_p)
+        self._ck(hostlib().nsh_get_solution(self.h, _p(out, C.c_double)))
+        return out
+
+    def device(self):
+        return _BorrowedDevice(hostlib().nsh_device(self.h), self.dim, self.n_u + self.n_p)
+
+    def close(self):
+        if self.h:
+            hostlib().nsh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -4,7 +4,8 @@
 #include "../../include/nsb200.h"
 
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is resolved at run time (see NcclApi)
 
 #include <algorithm>
 #include <cmath>
@@ -39,8 +40,44 @@ struct CudaErr {
   do {                                                                                   \
     ncclResult_t r_ = (call);                                                            \
     if (r_ != ncclSuccess)                                                               \
-      throw CudaErr{std::string(#call) + " failed: " + ncclGetErrorString(r_)};          \
+      throw CudaErr{std::string(#call) + " failed: " + g_nccl.GetErrorString(r_)};       \
   } while (0)
+
+// NCCL is bound lazily with dlopen so that libnsb200.so has no link-time dependency on a
+// particular libnccl.so.2: inside a PyTorch process the already-loaded (newer) NCCL is reused,
+// in a plain C++ program the system one is loaded.  Only needed with more than one rank.
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string& err) {
+    if (handle) return true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (handle) break;
+    }
+    if (!handle) { err = std::string("cannot load NCCL: ") + dlerror(); return false; }
+    auto sym = [&](const char* n) { void* p = dlsym(handle, n); if (!p) err = std::string("NCCL symbol missing: ") + n; return p; };
+    GetUniqueId = (decltype(GetUniqueId))sym("ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))sym("ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
+    AllReduce = (decltype(AllReduce))sym("ncclAllReduce");
+    Send = (decltype(Send))sym("ncclSend");
+    Recv = (decltype(Recv))sym("ncclRecv");
+    GroupStart = (decltype(GroupStart))sym("ncclGroupStart");
+    GroupEnd = (decltype(GroupEnd))sym("ncclGroupEnd");
+    GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
+    return GetUniqueId && CommInitRank && CommDestroy && AllReduce && Send && Recv && GroupStart && GroupEnd && GetErrorString;
+  }
+};
+NcclApi g_nccl;
 
 template <typename T> struct DBuf {
   T* p = nullptr;
@@ -233,24 +270,24 @@ void halo_exchange(nsb_ctx* c, double* v) {
     if (nu) { k_gather_nodes<<<nblk((long long)nu * S.dim, 256), 256, 0, c->stream>>>(nu, S.dim, B[k]->uoff.p, v, B[k]->u.p); c->launch_check(); }
     if (np) { k_gather<<<nblk(np, 256), 256, 0, c->stream>>>(np, B[k]->poff.p, v, B[k]->p.p); c->launch_check(); }
   }
-  CKN(ncclGroupStart());
+  CKN(g_nccl.GroupStart());
   long long uoff = S.n_own_dofs(), poff = S.n_own_dofs() + (long long)S.dim * S.nn_ghost;
   for (size_t k = 0; k < S.peer.size(); ++k) {
     const int peer = S.peer[k];
     const size_t nu = S.send_nodes[k].size() * S.dim, np = S.send_pids[k].size();
-    if (nu) CKN(ncclSend(B[k]->u.p, nu, ncclDouble, peer, c->comm, c->stream));
-    if (np) CKN(ncclSend(B[k]->p.p, np, ncclDouble, peer, c->comm, c->stream));
+    if (nu) CKN(g_nccl.Send(B[k]->u.p, nu, ncclDouble, peer, c->comm, c->stream));
+    if (np) CKN(g_nccl.Send(B[k]->p.p, np, ncclDouble, peer, c->comm, c->stream));
     const size_t ru = (size_t)S.recv_node_count[k] * S.dim, rp = (size_t)S.recv_pid_count[k];
-    if (ru) CKN(ncclRecv(v + uoff, ru, ncclDouble, peer, c->comm, c->stream));
-    if (rp) CKN(ncclRecv(v + poff, rp, ncclDouble, peer, c->comm, c->stream));
+    if (ru) CKN(g_nccl.Recv(v + uoff, ru, ncclDouble, peer, c->comm, c->stream));
+    if (rp) CKN(g_nccl.Recv(v + poff, rp, ncclDouble, peer, c->comm, c->stream));
     uoff += ru; poff += rp;
   }
-  CKN(ncclGroupEnd());
+  CKN(g_nccl.GroupEnd());
 }
 
 void allreduce_sum(nsb_ctx* c, double* dbuf, int n) {
   if (c->nranks == 1) return;
-  CKN(ncclAllReduce(dbuf, dbuf, n, ncclDouble, ncclSum, c->comm, c->stream));
+  CKN(g_nccl.AllReduce(dbuf, dbuf, n, ncclDouble, ncclSum, c->comm, c->stream));
 }
 
 // ---- templated launch helpers --------------------------------------------------------
@@ -876,7 +913,7 @@ int nsb_destroy(nsb_handle c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  if (c->comm) ncclCommDestroy(c->comm);
+  if (c->comm) g_nccl.CommDestroy(c->comm);
   if (c->t0) cudaEventDestroy(c->t0);
   if (c->t1) cudaEventDestroy(c->t1);
   cudaStream_t s = c->stream;
@@ -889,7 +926,9 @@ const char* nsb_last_error(nsb_handle c) { return c ? c->err.c_str() : "null han
 
 int nsb_comm_unique_id(void* out128) {
   ncclUniqueId id;
-  if (ncclGetUniqueId(&id) != ncclSuccess) return -1;
+  std::string err;
+  if (!g_nccl.load(err)) { std::fprintf(stderr, "nsb200: %s\n", err.c_str()); return -1; }
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return -1;
   std::memcpy(out128, &id, sizeof(id));
   return 0;
 }
@@ -900,9 +939,12 @@ int nsb_comm_init(nsb_handle c, int rank, int nranks, const void* uid) {
   CK(cudaSetDevice(c->device));
   if (c->have_mesh) throw CudaErr{"nsb_comm_init must precede nsb_upload_mesh"};
   if (nranks > 1) {
+    std::string err;
+    if (!g_nccl.load(err)) throw CudaErr{err};
+    if (!uid) throw CudaErr{"nccl_unique_id is required with more than one rank"};
     ncclUniqueId id;
     std::memcpy(&id, uid, sizeof(id));
-    CKN(ncclCommInitRank(&c->comm, nranks, id, rank));
+    CKN(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
   }
   c->rank = rank; c->nranks = nranks;
   return 0;
@@ -1164,7 +1206,7 @@ int nsb_assemble_pressure_matrices(nsb_handle c) {
       DBuf<double> tmp;
       std::vector<double> f(pflag.begin(), pflag.end());
       tmp.upload(f, st);
-      CKN(ncclAllReduce(tmp.p, tmp.p, f.size(), ncclDouble, ncclMax, c->comm, st));
+      CKN(g_nccl.AllReduce(tmp.p, tmp.p, f.size(), ncclDouble, ncclMax, c->comm, st));
       CK(cudaMemcpyAsync(f.data(), tmp.p, f.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       for (size_t i = 0; i < f.size(); ++i) pflag[i] = f[i] != 0.0;
@@ -1329,7 +1371,42 @@ int nsb_profile_get(nsb_handle c, const char* name, double* total_ms, int64_t* l
     }
   return fail(c, "unknown profile class");
 }
-/* host-only helper exported for the CPU test-suite: eigenvalues of an upper-Hessenberg matrix */
+/* host-only helpers exported for the CPU test-suite (no CUDA calls) ------------------------- */
+/* builds the node-block structure of `rank`/`nranks` and exports the owned rows as scalar CSR
+ * with global columns, the global row ids and the halo plan sizes.  Pass NULL arrays to query sizes. */
+int nsb_test_build_pattern(int dim, int64_t n_vertices, const double* coords, int64_t n_cells,
+                           const uint32_t* cell_vertices, const uint32_t* cell_dofs, int64_t n_u, int64_t n_p,
+                           const int32_t* cell_part, int rank, int nranks, int64_t* n_rows, int64_t* nnz,
+                           int64_t* rowptr, uint32_t* col, int64_t* row_gids, int64_t* n_ghost_dofs,
+                           int64_t* n_send_dofs, int64_t* n_local_cells) {
+  Structure S;
+  const std::string e = build_structure(dim, n_vertices, coords, n_cells, cell_vertices, cell_dofs, n_u, n_p, cell_part, rank, nranks, S);
+  if (!e.empty()) { std::fprintf(stderr, "nsb_test_build_pattern: %s\n", e.c_str()); return -1; }
+  if (n_rows) *n_rows = S.n_own_dofs();
+  if (nnz) *nnz = S.nnz_local;
+  if (n_ghost_dofs) *n_ghost_dofs = S.n_tot_dofs() - S.n_own_dofs();
+  if (n_local_cells) *n_local_cells = S.nc;
+  if (n_send_dofs) {
+    int64_t t = 0;
+    for (size_t k = 0; k < S.peer.size(); ++k) t += (int64_t)S.send_nodes[k].size() * dim + (int64_t)S.send_pids[k].size();
+    *n_send_dofs = t;
+  }
+  if (rowptr && col) {
+    std::vector<int64_t> rp;
+    std::vector<uint32_t> cl;
+    export_pattern(S, rp, cl);
+    std::copy(rp.begin(), rp.end(), rowptr);
+    std::copy(cl.begin(), cl.end(), col);
+  }
+  if (row_gids) {
+    std::vector<int64_t> g;
+    export_row_gids(S, g);
+    std::copy(g.begin(), g.end(), row_gids);
+  }
+  return 0;
+}
+
+/* eigenvalues of an upper-Hessenberg matrix */
 int nsb_test_hessenberg_eigs(int n, const double* a, double* wr, double* wi) {
   std::vector<double> A(a, a + (size_t)n * n), r, i;
   if (!hessenberg_eigs(n, A, r, i)) return 1;

@@ -1,0 +1,217 @@
+"""CPU: the C-ABI libraries load and export every declared symbol; the C++ host mirror reproduces the
+oracle's integer setup bit-exactly (DoF maps, sparsity, constraints); the node-block structure builder
+of the CUDA library exports the same scalar pattern, also when the mesh is split over ranks."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import dofs as odofs, postprocess as pp
+from tests.conftest import PKG_DIR, ROOT
+from tools import msh
+
+LIB = os.path.join(PKG_DIR, "libnsb200.so")
+HOSTLIB = os.path.join(PKG_DIR, "libnsbhost.so")
+
+
+def _declared(header, prefix):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(%s_[a-z0-9_]+)\s*\(" % prefix, txt)))
+
+
+def test_libraries_export_all_declared_symbols():
+    assert os.path.exists(LIB), "libnsb200.so missing: run __graft_entry__.build()"
+    lib = C.CDLL(LIB, mode=C.RTLD_GLOBAL)
+    names = _declared("nsb200.h", "nsb")
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), n
+    host = C.CDLL(HOSTLIB)
+    for n in _declared("nsb200_host.h", "nsh") + _declared("nsb200_host.h", "nshd"):
+        assert hasattr(host, n), n
+
+
+def test_no_cuda_device_fails_loudly(nsb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(nsb.NsbError):
+        nsb.Device(2)
+
+
+class HostSetup:
+    def __init__(self, path, dim):
+        C.CDLL(LIB, mode=C.RTLD_GLOBAL)
+        self.L = C.CDLL(HOSTLIB)
+        self.L.nsh_last_error.restype = C.c_char_p
+        self.h = C.c_void_p()
+        rc = self.L.nshd_create(path.encode(), dim, C.byref(self.h))
+        if rc != 0:
+            raise RuntimeError(self.L.nsh_last_error().decode())
+        self.dim = dim
+        v = [C.c_int64() for _ in range(5)]
+        self.L.nshd_get_sizes(self.h, *[C.byref(x) for x in v])
+        self.n_u, self.n_p, self.n_cells, self.n_vertices, self.n_bf = [x.value for x in v]
+
+    def cell_dofs(self):
+        dpc = self.dim * (6 if self.dim == 2 else 10) + self.dim + 1
+        a = np.empty((self.n_cells, dpc), np.uint32)
+        self.L.nshd_get_cell_dofs(self.h, a.ctypes.data_as(C.POINTER(C.c_uint32)))
+        return a
+
+    def support_points(self):
+        p = np.empty((self.n_u + self.n_p, self.dim))
+        c = np.empty(self.n_u + self.n_p, np.uint8)
+        self.L.nshd_get_support_points(self.h, p.ctypes.data_as(C.POINTER(C.c_double)), c.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        return p, c
+
+    def pattern(self):
+        nnz = C.c_int64()
+        self.L.nshd_get_pattern(self.h, C.byref(nnz), None, None)
+        rp = np.empty(self.n_u + self.n_p + 1, np.int64)
+        col = np.empty(nnz.value, np.uint32)
+        self.L.nshd_get_pattern(self.h, C.byref(nnz), rp.ctypes.data_as(C.POINTER(C.c_int64)), col.ctypes.data_as(C.POINTER(C.c_uint32)))
+        return rp, col
+
+    def constraints(self, case, t, homogeneous):
+        n = C.c_int64()
+        assert self.L.nshd_get_constraints(self.h, case.encode(), C.c_double(t), int(homogeneous), C.byref(n), None, None) == 0
+        d = np.empty(n.value, np.uint32)
+        v = np.empty(n.value)
+        self.L.nshd_get_constraints(self.h, case.encode(), C.c_double(t), int(homogeneous), C.byref(n),
+                                    d.ctypes.data_as(C.POINTER(C.c_uint32)), v.ctypes.data_as(C.POINTER(C.c_double)))
+        return d, v
+
+    def mesh(self):
+        p = np.empty((self.n_vertices, self.dim))
+        c = np.empty((self.n_cells, self.dim + 1), np.uint32)
+        self.L.nshd_get_mesh(self.h, p.ctypes.data_as(C.POINTER(C.c_double)), c.ctypes.data_as(C.POINTER(C.c_uint32)))
+        return p, c
+
+    def __del__(self):
+        try:
+            self.L.nshd_destroy(self.h)
+        except Exception:
+            pass
+
+
+@pytest.mark.parametrize("name", ["mesh-2D", "mesh-2D-40"])
+def test_host_dofs_sparsity_constraints_bit_exact(golden_mesh, msh_file, name):
+    m = golden_mesh(name)
+    hs = HostSetup(msh_file(name), 2)
+    dm = odofs.enumerate_dofs(m)
+    assert (hs.n_u, hs.n_p, hs.n_cells) == (dm.n_u, dm.n_p, m.n_cells)
+    assert np.array_equal(hs.cell_dofs(), dm.cell_dofs.astype(np.uint32))
+    p, c = hs.support_points()
+    assert np.array_equal(p, dm.support_points) and np.array_equal(c, dm.component.astype(np.uint8))
+    rp, col = hs.pattern()
+    orp, ocol = odofs.make_sparsity(dm)
+    assert np.array_equal(rp, orp) and np.array_equal(col.astype(np.int64), ocol.astype(np.int64))
+    ids = pp.boundary_ids(2)
+    for case, t, hom in (("2D-2", 1.0, False), ("2D-3", 3.0, False), ("2D-1", 0.5, True)):
+        tc = pp.TEST_CASES[case]
+        con = odofs.build_constraints(m, dm, pp.inlet_profile(2, tc["U_m"], tc["time_dep"], tc["T_ramp"], t), ids, homogeneous=hom)
+        d, v = hs.constraints(case, t, hom)
+        assert np.array_equal(d.astype(np.int64), con.dofs)
+        assert np.array_equal(v, con.val[con.dofs])
+
+
+def test_host_3d_setup_matches_oracle(small_3d_mesh, tmp_path):
+    m = small_3d_mesh
+    path = str(tmp_path / "m3.bin")
+    msh.write_bin(path, m)
+    hs = HostSetup(path, 3)
+    dm = odofs.enumerate_dofs(m)
+    assert np.array_equal(hs.cell_dofs(), dm.cell_dofs.astype(np.uint32))
+    ids = pp.boundary_ids(3)
+    con = odofs.build_constraints(m, dm, pp.inlet_profile(3, 2.25, False, 4.0, 2.0), ids)
+    d, v = hs.constraints("3D-2Z", 2.0, False)
+    assert np.array_equal(d.astype(np.int64), con.dofs) and np.array_equal(v, con.val[con.dofs])
+    # the ASCII writer / reader round trip gives the same mesh
+    path2 = str(tmp_path / "m3.msh")
+    msh.write_msh(path2, m)
+    hs2 = HostSetup(path2, 3)
+    p, c = hs2.mesh()
+    assert np.array_equal(p, m.points) and np.array_equal(c, m.cells.astype(np.uint32))
+    assert np.array_equal(hs2.cell_dofs(), hs.cell_dofs())
+
+
+def test_msh_reader_prepass(golden_mesh, tmp_path):
+    """$ParametricNodes blocks and CRLF line ends are accepted (reference cpp:16-51)."""
+    m = golden_mesh("mesh-2D")
+    path = str(tmp_path / "a.msh")
+    msh.write_msh(path, m)
+    txt = open(path).read()
+    nodes = txt[txt.index("$Nodes"):txt.index("$EndNodes")]
+    lines = nodes.split("\n")
+    par = ["$ParametricNodes", lines[1]] + [ln + " 1 7 0.25" for ln in lines[2:] if ln]
+    txt2 = txt.replace(nodes + "$EndNodes", "\n".join(par) + "\n$EndParametricNodes").replace("\n", "\r\n")
+    path2 = str(tmp_path / "b.msh")
+    open(path2, "w", newline="").write(txt2)
+    a, b = HostSetup(path, 2), HostSetup(path2, 2)
+    assert np.array_equal(a.cell_dofs(), b.cell_dofs())
+    assert np.array_equal(a.mesh()[0], b.mesh()[0])
+    m2 = msh.read_msh(path2)
+    assert np.array_equal(m2.cells, m.cells) and np.allclose(m2.points, m.points, rtol=0, atol=0)
+    with pytest.raises(RuntimeError, match="Could not open mesh file"):
+        HostSetup(str(tmp_path / "missing.msh"), 2)
+
+
+def _build_pattern(lib, dim, m, dm, part, rank, nranks):
+    pts = np.ascontiguousarray(m.points, np.float64)
+    cv = np.ascontiguousarray(m.cells, np.uint32)
+    cd = np.ascontiguousarray(dm.cell_dofs, np.uint32)
+    pa = None if part is None else np.ascontiguousarray(part, np.int32)
+    P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    n, nnz, ng, ns, nc = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+    args = (dim, C.c_int64(pts.shape[0]), P(pts, C.c_double), C.c_int64(cv.shape[0]), P(cv, C.c_uint32), P(cd, C.c_uint32),
+            C.c_int64(dm.n_u), C.c_int64(dm.n_p), P(pa, C.c_int32) if pa is not None else None, rank, nranks)
+    assert lib.nsb_test_build_pattern(*args, C.byref(n), C.byref(nnz), None, None, None, C.byref(ng), C.byref(ns), C.byref(nc)) == 0
+    rp = np.empty(n.value + 1, np.int64)
+    col = np.empty(nnz.value, np.uint32)
+    gid = np.empty(n.value, np.int64)
+    assert lib.nsb_test_build_pattern(*args, C.byref(n), C.byref(nnz), P(rp, C.c_int64), P(col, C.c_uint32), P(gid, C.c_int64),
+                                      C.byref(ng), C.byref(ns), C.byref(nc)) == 0
+    return rp, col, gid, ng.value, ns.value, nc.value
+
+
+@pytest.mark.parametrize("which", ["2d", "3d"])
+def test_device_structure_pattern_bit_exact_and_partition_invariant(golden_mesh, small_3d_mesh, which):
+    lib = C.CDLL(LIB, mode=C.RTLD_GLOBAL)
+    m = golden_mesh("mesh-2D") if which == "2d" else small_3d_mesh
+    dim = m.dim
+    dm = odofs.enumerate_dofs(m)
+    orp, ocol = odofs.make_sparsity(dm)
+    rp, col, gid, ng, ns, nc = _build_pattern(lib, dim, m, dm, None, 0, 1)
+    assert np.array_equal(gid, np.arange(dm.n_dofs)) and ng == 0 and ns == 0 and nc == m.n_cells
+    assert np.array_equal(rp, orp) and np.array_equal(col.astype(np.int64), ocol.astype(np.int64))
+    # split into R contiguous chunks: rows are partitioned, every row keeps exactly its global pattern
+    for R in (2, 4):
+        part = (np.arange(m.n_cells) * R) // m.n_cells
+        seen = np.zeros(dm.n_dofs, int)
+        ghosts, sends = 0, 0
+        for r in range(R):
+            rp, col, gid, ng, ns, nc = _build_pattern(lib, dim, m, dm, part, r, R)
+            seen[gid] += 1
+            for k in range(0, gid.size, max(1, gid.size // 400)):
+                g = gid[k]
+                assert np.array_equal(col[rp[k]:rp[k + 1]].astype(np.int64), ocol[orp[g]:orp[g + 1]].astype(np.int64))
+            assert np.array_equal(np.diff(rp), np.diff(orp)[gid])
+            ghosts += ng
+            sends += ns
+        assert np.all(seen == 1)
+        assert ghosts == sends and ghosts > 0          # every ghost DoF is sent by exactly one owner
+
+
+def test_hessenberg_eigenvalues():
+    lib = C.CDLL(LIB, mode=C.RTLD_GLOBAL)
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 5, 9, 16, 33):
+        A = np.triu(rng.standard_normal((n, n)), -1)
+        wr, wi = np.zeros(n), np.zeros(n)
+        P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        assert lib.nsb_test_hessenberg_eigs(n, P(A), P(wr), P(wi)) == 0
+        assert np.abs(np.sort_complex(np.linalg.eigvals(A)) - np.sort_complex(wr + 1j * wi)).max() < 1e-11

