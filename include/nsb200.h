@@ -71,6 +71,9 @@ int nsb_upload_mesh(nsb_handle h, int64_t n_vertices, const double* coords, int6
                     const int32_t* cell_part);
 /* local sizes: owned rows, stored non-zeros of the owned rows, local cells (owned + ghost layer) */
 int nsb_get_sizes(nsb_handle h, int64_t* n_rows_owned, int64_t* nnz_owned, int64_t* n_cells_local);
+/* stored non-zeros of the owned rows per block: velocity-velocity (F), velocity-pressure (B^T),
+ * pressure-velocity (B), pressure-pressure */
+int nsb_get_block_nnz(nsb_handle h, int64_t* uu, int64_t* up, int64_t* pu, int64_t* pp);
 /* sparsity pattern of the owned rows as scalar CSR with GLOBAL column indices, rows in local
  * order (see nsb_get_row_gids); on one GPU this is exactly make_sparsity_pattern's result
  * (cpp:265).  rowptr[n_rows_owned+1], col[nnz_owned]. */

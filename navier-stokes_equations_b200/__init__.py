@@ -112,6 +112,11 @@ class Device:
         self._ck(lib().nsb_get_sizes(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def block_nnz(self):
+        v = [C.c_int64() for _ in range(4)]
+        self._ck(lib().nsb_get_block_nnz(self.h, *[C.byref(x) for x in v]))
+        return dict(uu=v[0].value, up=v[1].value, pu=v[2].value, pp=v[3].value)
+
     def pattern(self):
         n, nnz, _ = self.sizes()
         rp = np.empty(n + 1, np.int64)
@@ -318,6 +323,69 @@ class HostSolver:
     def close(self):
         if self.h:
             hostlib().nsh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HostSetup:
+    """Host-only setup object (nshd_*): mesh reading, DoF enumeration, sparsity, constraints -- the
+    integer part of the reference's setup(), no GPU involved."""
+
+    def __init__(self, mesh_file, dim):
+        L = hostlib()
+        self.h = C.c_void_p()
+        if L.nshd_create(mesh_file.encode(), dim, C.byref(self.h)) != 0:
+            raise NsbError(L.nsh_last_error().decode())
+        self.dim = dim
+        v = [C.c_int64() for _ in range(5)]
+        L.nshd_get_sizes(self.h, *[C.byref(x) for x in v])
+        self.n_u, self.n_p, self.n_cells, self.n_vertices, self.n_boundary_faces = [x.value for x in v]
+        self.n_dofs = self.n_u + self.n_p
+        self.dofs_per_cell = dim * (6 if dim == 2 else 10) + dim + 1
+
+    def cell_dofs(self):
+        a = np.empty((self.n_cells, self.dofs_per_cell), np.uint32)
+        hostlib().nshd_get_cell_dofs(self.h, _p(a, C.c_uint32))
+        return a
+
+    def support_points(self):
+        p = np.empty((self.n_dofs, self.dim))
+        c = np.empty(self.n_dofs, np.uint8)
+        hostlib().nshd_get_support_points(self.h, _p(p, C.c_double), _p(c, C.c_ubyte))
+        return p, c
+
+    def pattern(self):
+        nnz = C.c_int64()
+        if hostlib().nshd_get_pattern(self.h, C.byref(nnz), None, None) != 0:
+            raise NsbError(hostlib().nsh_last_error().decode())
+        rp = np.empty(self.n_dofs + 1, np.int64)
+        col = np.empty(nnz.value, np.uint32)
+        hostlib().nshd_get_pattern(self.h, C.byref(nnz), _p(rp, C.c_int64), _p(col, C.c_uint32))
+        return rp, col
+
+    def constraints(self, case, t, homogeneous=False):
+        n = C.c_int64()
+        if hostlib().nshd_get_constraints(self.h, case.encode(), C.c_double(t), int(homogeneous), C.byref(n), None, None) != 0:
+            raise NsbError(hostlib().nsh_last_error().decode())
+        d = np.empty(n.value, np.uint32)
+        v = np.empty(n.value)
+        hostlib().nshd_get_constraints(self.h, case.encode(), C.c_double(t), int(homogeneous), C.byref(n), _p(d, C.c_uint32), _p(v, C.c_double))
+        return d, v
+
+    def mesh(self):
+        p = np.empty((self.n_vertices, self.dim))
+        c = np.empty((self.n_cells, self.dim + 1), np.uint32)
+        hostlib().nshd_get_mesh(self.h, _p(p, C.c_double), _p(c, C.c_uint32))
+        return p, c
+
+    def close(self):
+        if self.h:
+            hostlib().nshd_destroy(self.h)
             self.h = None
 
     def __del__(self):

@@ -210,6 +210,7 @@ struct nsb_ctx {
   double Mp_lmax = 1.0;
   std::vector<std::unique_ptr<DevLevel>> amg;
   std::vector<std::unique_ptr<HaloBuf>> halo;
+  double* pin = nullptr;           // pinned staging buffer for host <-> device vector traffic (n_tot doubles)
   DBuf<double> coarse_inv;
   int coarse_n = 0;
   // preconditioner / Krylov workspace
@@ -913,6 +914,7 @@ int nsb_destroy(nsb_handle c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->pin) cudaFreeHost(c->pin);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   if (c->t0) cudaEventDestroy(c->t0);
   if (c->t1) cudaEventDestroy(c->t1);
@@ -1020,6 +1022,8 @@ int nsb_upload_mesh(nsb_handle c, int64_t n_vertices, const double* coords, int6
     v->alloc(nt);
     v->zero(st);
   }
+  if (c->pin) { cudaFreeHost(c->pin); c->pin = nullptr; }
+  CK(cudaMallocHost(&c->pin, nt * sizeof(double)));
   c->cflag.alloc(nt); c->cflag.zero(st);
   c->vals.alloc((size_t)S.nnz_local);
   c->dinv.alloc((size_t)S.nn_own * dim * dim);
@@ -1038,6 +1042,23 @@ int nsb_get_sizes(nsb_handle c, int64_t* nrows, int64_t* nnz, int64_t* ncl) {
   if (nrows) *nrows = c->S.n_own_dofs();
   if (nnz) *nnz = c->S.nnz_local;
   if (ncl) *ncl = c->S.nc;
+  return 0;
+}
+
+int nsb_get_block_nnz(nsb_handle c, int64_t* uu, int64_t* up, int64_t* pu, int64_t* pp) {
+  if (!c || !c->have_mesh) return fail(c, "no mesh uploaded");
+  const Structure& S = c->S;
+  int64_t a = 0, b = 0, d = 0, e = 0;
+  for (int A = 0; A < S.nn_own; ++A) {
+    const int64_t nb = S.nbr_ptr[A + 1] - S.nbr_ptr[A], np = S.pnbr_ptr[A + 1] - S.pnbr_ptr[A];
+    a += (int64_t)S.dim * S.dim * nb;
+    b += (int64_t)S.dim * np;
+    if (S.node_pid[A] >= 0) { d += (int64_t)S.dim * nb; e += np; }
+  }
+  if (uu) *uu = a;
+  if (up) *up = b;
+  if (pu) *pu = d;
+  if (pp) *pp = e;
   return 0;
 }
 
@@ -1120,12 +1141,18 @@ int nsb_set_vector(nsb_handle c, int which, const double* vg) {
   double* d = vec_ptr(c, which);
   if (!d) return fail(c, "bad vector id");
   const Structure& S = c->S;
-  std::vector<double> loc(S.n_tot_dofs());
+  double* loc = c->pin;
   const int dim = c->dim;
-  for (int A = 0; A < S.nn_own + S.nn_ghost; ++A)
-    for (int k = 0; k < dim; ++k) loc[S.node_xoff(A) + k] = vg[S.node_gid[A] * dim + k];
-  for (int P = 0; P < S.np_own + S.np_ghost; ++P) loc[S.pid_xoff(P)] = vg[c->n_u + S.pid_gid[P]];
-  CK(cudaMemcpyAsync(d, loc.data(), loc.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (c->nranks == 1) {
+    std::memcpy(loc, vg, (size_t)S.n_own_dofs() * sizeof(double));     // local layout == global numbering
+  } else {
+#pragma omp parallel for schedule(static)
+    for (int A = 0; A < S.nn_own + S.nn_ghost; ++A)
+      for (int k = 0; k < dim; ++k) loc[S.node_xoff(A) + k] = vg[S.node_gid[A] * dim + k];
+#pragma omp parallel for schedule(static)
+    for (int P = 0; P < S.np_own + S.np_ghost; ++P) loc[S.pid_xoff(P)] = vg[c->n_u + S.pid_gid[P]];
+  }
+  CK(cudaMemcpyAsync(d, loc, (size_t)S.n_tot_dofs() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return 0;
   NSB_CATCH(c)
@@ -1138,13 +1165,17 @@ int nsb_get_vector(nsb_handle c, int which, double* vg) {
   double* d = vec_ptr(c, which);
   if (!d) return fail(c, "bad vector id");
   const Structure& S = c->S;
-  std::vector<double> loc(S.n_own_dofs());
-  CK(cudaMemcpyAsync(loc.data(), d, loc.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  double* loc = c->pin;
+  CK(cudaMemcpyAsync(loc, d, (size_t)S.n_own_dofs() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   const int dim = c->dim;
-  for (int A = 0; A < S.nn_own; ++A)
-    for (int k = 0; k < dim; ++k) vg[S.node_gid[A] * dim + k] = loc[(size_t)dim * A + k];
-  for (int P = 0; P < S.np_own; ++P) vg[c->n_u + S.pid_gid[P]] = loc[(size_t)dim * S.nn_own + P];
+  if (c->nranks == 1) {
+    std::memcpy(vg, loc, (size_t)S.n_own_dofs() * sizeof(double));
+  } else {
+    for (int A = 0; A < S.nn_own; ++A)
+      for (int k = 0; k < dim; ++k) vg[S.node_gid[A] * dim + k] = loc[(size_t)dim * A + k];
+    for (int P = 0; P < S.np_own; ++P) vg[c->n_u + S.pid_gid[P]] = loc[(size_t)dim * S.nn_own + P];
+  }
   return 0;
   NSB_CATCH(c)
 }

@@ -104,6 +104,13 @@ class BlockTriangular:
             self.Finv = spla.splu(F).solve
             self.Mpinv = spla.splu(Mp11).solve
             self.Kpinv = spla.splu(Kp11).solve
+        elif inner == "ilu":
+            # incomplete factorizations as in the reference (Ifpack ILU(1) on F, ILU(0) on M_p; hpp:302-307);
+            # SuperLU's threshold ILU stands in for the level-of-fill variants.  K_p (ML AMG in the
+            # reference, hpp:310-315) is factorized exactly: it is small and constant.
+            self.Finv = spla.spilu(F, drop_tol=1e-4, fill_factor=2.0).solve
+            self.Mpinv = spla.spilu(Mp11, drop_tol=0.0, fill_factor=1.0).solve
+            self.Kpinv = spla.splu(Kp11).solve
         else:
             raise ValueError(inner)
 

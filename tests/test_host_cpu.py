@@ -42,60 +42,13 @@ def test_no_cuda_device_fails_loudly(nsb):
         nsb.Device(2)
 
 
-class HostSetup:
-    def __init__(self, path, dim):
-        C.CDLL(LIB, mode=C.RTLD_GLOBAL)
-        self.L = C.CDLL(HOSTLIB)
-        self.L.nsh_last_error.restype = C.c_char_p
-        self.h = C.c_void_p()
-        rc = self.L.nshd_create(path.encode(), dim, C.byref(self.h))
-        if rc != 0:
-            raise RuntimeError(self.L.nsh_last_error().decode())
-        self.dim = dim
-        v = [C.c_int64() for _ in range(5)]
-        self.L.nshd_get_sizes(self.h, *[C.byref(x) for x in v])
-        self.n_u, self.n_p, self.n_cells, self.n_vertices, self.n_bf = [x.value for x in v]
-
-    def cell_dofs(self):
-        dpc = self.dim * (6 if self.dim == 2 else 10) + self.dim + 1
-        a = np.empty((self.n_cells, dpc), np.uint32)
-        self.L.nshd_get_cell_dofs(self.h, a.ctypes.data_as(C.POINTER(C.c_uint32)))
-        return a
-
-    def support_points(self):
-        p = np.empty((self.n_u + self.n_p, self.dim))
-        c = np.empty(self.n_u + self.n_p, np.uint8)
-        self.L.nshd_get_support_points(self.h, p.ctypes.data_as(C.POINTER(C.c_double)), c.ctypes.data_as(C.POINTER(C.c_ubyte)))
-        return p, c
-
-    def pattern(self):
-        nnz = C.c_int64()
-        self.L.nshd_get_pattern(self.h, C.byref(nnz), None, None)
-        rp = np.empty(self.n_u + self.n_p + 1, np.int64)
-        col = np.empty(nnz.value, np.uint32)
-        self.L.nshd_get_pattern(self.h, C.byref(nnz), rp.ctypes.data_as(C.POINTER(C.c_int64)), col.ctypes.data_as(C.POINTER(C.c_uint32)))
-        return rp, col
-
-    def constraints(self, case, t, homogeneous):
-        n = C.c_int64()
-        assert self.L.nshd_get_constraints(self.h, case.encode(), C.c_double(t), int(homogeneous), C.byref(n), None, None) == 0
-        d = np.empty(n.value, np.uint32)
-        v = np.empty(n.value)
-        self.L.nshd_get_constraints(self.h, case.encode(), C.c_double(t), int(homogeneous), C.byref(n),
-                                    d.ctypes.data_as(C.POINTER(C.c_uint32)), v.ctypes.data_as(C.POINTER(C.c_double)))
-        return d, v
-
-    def mesh(self):
-        p = np.empty((self.n_vertices, self.dim))
-        c = np.empty((self.n_cells, self.dim + 1), np.uint32)
-        self.L.nshd_get_mesh(self.h, p.ctypes.data_as(C.POINTER(C.c_double)), c.ctypes.data_as(C.POINTER(C.c_uint32)))
-        return p, c
-
-    def __del__(self):
-        try:
-            self.L.nshd_destroy(self.h)
-        except Exception:
-            pass
+def HostSetup(path, dim):
+    from tests.conftest import load_nsb
+    nsb = load_nsb()
+    try:
+        return nsb.HostSetup(path, dim)
+    except nsb.NsbError as e:
+        raise RuntimeError(str(e))
 
 
 @pytest.mark.parametrize("name", ["mesh-2D", "mesh-2D-40"])
