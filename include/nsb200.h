@@ -47,6 +47,9 @@ typedef struct nsb_solver_opts {
   double schur_mass_coeff;  /* coefficient of M_p^-1; <0 = theta*nu + gamma_graddiv (default),
                                set to theta*nu for the reference's exact scaling (hpp:343) */
   int32_t reorthogonalize;  /* 1 = classical Gram-Schmidt twice (default), 0 = once        */
+  int32_t precond_precision;/* storage of the operator used INSIDE the velocity polynomial: 32 (default; products are
+                               accumulated in fp64, so the preconditioner stays a fixed linear operator) or 64.
+                               Changing it invalidates the assembled system (re-assemble before solving). */
 } nsb_solver_opts;
 
 /* ---- lifetime -------------------------------------------------------------------- */

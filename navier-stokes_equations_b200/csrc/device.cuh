@@ -10,8 +10,19 @@ namespace nsb {
 
 #define NSB_FULL 0xffffffffu
 
+// Per owned node, everything a row kernel needs, in one 32-byte record (two 128-bit loads).
+struct __align__(16) NodeDesc {
+  long long rowbase;      // offset of scalar row (node,0) in the value array
+  long long prowbase;     // offset of the node's pressure row (vertex nodes), else 0
+  int nbr0;               // first entry of the node's neighbour list in nbr_xoff
+  int pnbr0;              // first entry in pnbr_xoff
+  unsigned short nb, np;  // neighbour counts (velocity nodes / pressure DoFs)
+  int pid;                // local pressure id of a vertex node, -1 otherwise
+};
+
 // Everything the kernels need to know about the (local) mesh + sparse structure.
 struct DevMesh {
+  const NodeDesc* nd;                   // [nn_own]
   int dim, nn_own, nn_tot, np_own, np_tot, nc;
   long long n_own, n_tot;               // local vector lengths (owned / owned+ghost)
   // cells

@@ -14,43 +14,101 @@ namespace nsb {
 constexpr int SPMV_WARPS = 8;
 
 // ------------------------------------------------------------------------------------
-// y = A x over the node-block structure.  One warp per owned P2 node handles the node's
+// Row kernels over the node-block structure.  One warp per owned P2 node handles the node's
 // dim velocity rows (+ its pressure row when the node is a vertex): the rows share the
 // column set, so x is gathered once and every matrix value is streamed exactly once,
-// contiguously per row (coalesced 256-byte warp loads, evict-first).
+// contiguously per row (coalesced warp loads, evict-first).  Columns are processed in
+// chunks of 32*SPMV_UNROLL with all loads of a chunk issued before the first use, which is
+// what keeps enough bytes in flight (the kernel is latency-, not instruction-bound).
 // ------------------------------------------------------------------------------------
+constexpr int SPMV_UNROLL = 4;
+
+__device__ __forceinline__ NodeDesc load_desc(const NodeDesc* p) {
+  const int4* q = reinterpret_cast<const int4*>(p);
+  const int4 a = __ldg(q), b = __ldg(q + 1);
+  NodeDesc d;
+  d.rowbase = ((long long)(unsigned)a.y << 32) | (unsigned)a.x;
+  d.prowbase = ((long long)(unsigned)a.w << 32) | (unsigned)a.z;
+  d.nbr0 = b.x; d.pnbr0 = b.y;
+  d.nb = (unsigned short)(b.z & 0xffff); d.np = (unsigned short)((unsigned)b.z >> 16);
+  d.pid = b.w;
+  return d;
+}
+
+// sum[r] += sum_k row_r[k] * x[col(k)] for k in [0, ncols); rows r < ROWS at rowptr[r].
+// Columns k < nbd are velocity columns (DIM per neighbour node), the rest pressure columns.
+template <int DIM, int ROWS, typename VT>
+__device__ __forceinline__ void row_block_dot(const VT* const (&rowp)[ROWS], int ncols, int nbd, const int* __restrict__ nx,
+                                              const int* __restrict__ px, const double* __restrict__ x, int lane,
+                                              double (&sum)[ROWS]) {
+  for (int k0 = 0; k0 < ncols; k0 += 32 * SPMV_UNROLL) {
+    VT v[ROWS][SPMV_UNROLL];
+    int xo[SPMV_UNROLL];
+    double xv[SPMV_UNROLL];
+#pragma unroll
+    for (int u = 0; u < SPMV_UNROLL; ++u) {
+      const int k = k0 + 32 * u + lane;
+      const bool ok = k < ncols;
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) v[r][u] = ok ? __ldcs(rowp[r] + k) : VT(0);
+      xo[u] = -1;
+      if (ok) xo[u] = (k < nbd) ? (__ldg(nx + k / DIM) + k % DIM) : __ldg(px + (k - nbd));
+    }
+#pragma unroll
+    for (int u = 0; u < SPMV_UNROLL; ++u) xv[u] = xo[u] >= 0 ? __ldg(x + xo[u]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < SPMV_UNROLL; ++u)
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) sum[r] += (double)v[r][u] * xv[u];
+  }
+}
+
+// y = A x
 template <int DIM, typename VT>
 __global__ void __launch_bounds__(SPMV_WARPS * 32)
 k_spmv_full(DevMesh M, const VT* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y) {
   const int lane = threadIdx.x & 31;
   const int A = blockIdx.x * SPMV_WARPS + (threadIdx.x >> 5);
   if (A >= M.nn_own) return;
-  const long long n0 = M.nbr_ptr[A], p0 = M.pnbr_ptr[A];
-  const int nb = (int)(M.nbr_ptr[A + 1] - n0), np = (int)(M.pnbr_ptr[A + 1] - p0);
-  const int nbd = DIM * nb, len = nbd + np;
-  const int pid = M.node_pid[A];
-  const bool isv = pid >= 0;
-  const VT* r0 = vals + M.rowbase[A];
-  const VT* rp = isv ? vals + M.prowbase[pid] : vals;
-  double sum[DIM + 1];
+  const NodeDesc d = load_desc(M.nd + A);
+  const int nbd = DIM * d.nb, len = nbd + d.np;
+  const int* nx = M.nbr_xoff + d.nbr0;
+  const int* px = M.pnbr_xoff + d.pnbr0;
+  if (d.pid >= 0) {
+    const VT* rowp[DIM + 1];
 #pragma unroll
-  for (int c = 0; c <= DIM; ++c) sum[c] = 0.0;
-  for (int k = lane; k < len; k += 32) {
-    const int xo = (k < nbd) ? (__ldg(M.nbr_xoff + n0 + k / DIM) + k % DIM) : __ldg(M.pnbr_xoff + p0 + (k - nbd));
-    const double xv = __ldg(x + xo);
+    for (int c = 0; c < DIM; ++c) rowp[c] = vals + d.rowbase + (long long)c * len;
+    rowp[DIM] = vals + d.prowbase;
+    double sum[DIM + 1];
 #pragma unroll
-    for (int c = 0; c < DIM; ++c) sum[c] += (double)__ldcs(r0 + (long long)c * len + k) * xv;
-    if (isv) sum[DIM] += (double)__ldcs(rp + k) * xv;
+    for (int c = 0; c <= DIM; ++c) sum[c] = 0.0;
+    row_block_dot<DIM, DIM + 1, VT>(rowp, len, nbd, nx, px, x, lane, sum);
+#pragma unroll
+    for (int c = 0; c <= DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
+    if (lane <= DIM) {
+      double v = sum[0];
+#pragma unroll
+      for (int c = 1; c <= DIM; ++c) if (lane == c) v = sum[c];
+      if (lane < DIM) y[DIM * A + lane] = v;
+      else y[DIM * M.nn_own + d.pid] = v;
+    }
+  } else {
+    const VT* rowp[DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) rowp[c] = vals + d.rowbase + (long long)c * len;
+    double sum[DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) sum[c] = 0.0;
+    row_block_dot<DIM, DIM, VT>(rowp, len, nbd, nx, px, x, lane, sum);
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
+    if (lane < DIM) {
+      double v = sum[0];
+#pragma unroll
+      for (int c = 1; c < DIM; ++c) if (lane == c) v = sum[c];
+      y[DIM * A + lane] = v;
+    }
   }
-#pragma unroll
-  for (int c = 0; c <= DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
-  if (lane < DIM) {
-    double v = sum[0];
-#pragma unroll
-    for (int c = 1; c < DIM; ++c) if (lane == c) v = sum[c];
-    y[DIM * A + lane] = v;
-  }
-  if (isv && lane == DIM) y[DIM * M.nn_own + pid] = sum[DIM];
 }
 
 // ------------------------------------------------------------------------------------
@@ -73,19 +131,15 @@ k_spmv_vel(DevMesh M, const VT* __restrict__ vals, const double* __restrict__ x,
   const int lane = threadIdx.x & 31;
   const int A = blockIdx.x * SPMV_WARPS + (threadIdx.x >> 5);
   if (A >= M.nn_own) return;
-  const long long n0 = M.nbr_ptr[A];
-  const int nb = (int)(M.nbr_ptr[A + 1] - n0);
-  const int nbd = DIM * nb;
-  const int len = nbd + (int)(M.pnbr_ptr[A + 1] - M.pnbr_ptr[A]);
-  const VT* r0 = vals + M.rowbase[A];
+  const NodeDesc d = load_desc(M.nd + A);
+  const int nbd = DIM * d.nb, len = nbd + d.np;
+  const VT* rowp[DIM];
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) rowp[c] = vals + d.rowbase + (long long)c * len;
   double sum[DIM];
 #pragma unroll
   for (int c = 0; c < DIM; ++c) sum[c] = 0.0;
-  for (int k = lane; k < nbd; k += 32) {
-    const double xv = __ldg(x + __ldg(M.nbr_xoff + n0 + k / DIM) + k % DIM);
-#pragma unroll
-    for (int c = 0; c < DIM; ++c) sum[c] += (double)__ldcs(r0 + (long long)c * len + k) * xv;
-  }
+  row_block_dot<DIM, DIM, VT>(rowp, nbd, nbd, M.nbr_xoff + d.nbr0, nullptr, x, lane, sum);
 #pragma unroll
   for (int c = 0; c < DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
   if (lane < DIM) {
@@ -119,15 +173,13 @@ k_schur_rhs(DevMesh M, const VT* __restrict__ vals, const double* __restrict__ y
   const int lane = threadIdx.x & 31;
   const int Pid = blockIdx.x * SPMV_WARPS + (threadIdx.x >> 5);
   if (Pid >= M.np_own) return;
-  const int A = M.pid_node[Pid];
-  const long long n0 = M.nbr_ptr[A];
-  const int nbd = DIM * (int)(M.nbr_ptr[A + 1] - n0);
-  const VT* rp = vals + M.prowbase[Pid];
-  double s = 0.0;
-  for (int k = lane; k < nbd; k += 32)
-    s += (double)__ldcs(rp + k) * __ldg(y0 + __ldg(M.nbr_xoff + n0 + k / DIM) + k % DIM);
-  s = warp_sum_fixed(s);
-  if (lane == 0) t[Pid] = g[DIM * M.nn_own + Pid] - s;
+  const NodeDesc d = load_desc(M.nd + M.pid_node[Pid]);
+  const int nbd = DIM * d.nb;
+  const VT* rowp[1] = {vals + d.prowbase};
+  double s[1] = {0.0};
+  row_block_dot<DIM, 1, VT>(rowp, nbd, nbd, M.nbr_xoff + d.nbr0, nullptr, y0, lane, s);
+  const double r = warp_sum_fixed(s[0]);
+  if (lane == 0) t[Pid] = g[DIM * M.nn_own + Pid] - r;
 }
 
 // y = Dinv x (node-block Jacobi scaling of a velocity vector)

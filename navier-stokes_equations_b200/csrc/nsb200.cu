@@ -186,6 +186,7 @@ struct nsb_ctx {
   DBuf<uint16_t> d_rank_uu, d_rank_up;
   DBuf<long long> d_nbr_ptr, d_pnbr_ptr, d_rowbase, d_prowbase, d_n2c_ptr;
   DBuf<uint32_t> d_n2c;
+  DBuf<NodeDesc> d_nd;
   int n_tiles = 0, tile_smem_bytes = 0;
   // global dof -> local vector offset (or -1)
   std::vector<int> g2x;
@@ -201,6 +202,7 @@ struct nsb_ctx {
   nsb_params par{};
   nsb_solver_opts opt{};
   DBuf<double> vals, dinv, ctx, cell_rhs;
+  DBuf<float> vals_f;               // fp32 copy of the values: operator of the velocity polynomial
   int ctx_stride = 0;
   // pressure matrices (global, replicated)
   HostCsr h_Mp, h_Kp;
@@ -312,7 +314,7 @@ template <int DIM> void launch_assemble(nsb_ctx* c, bool newton) {
     k_cell_context<DIM, false><<<nblk(c->S.nc, ASM_WARPS), ASM_WARPS * 32, 0, c->stream>>>(c->M, P, vecA, vecB, c->ctx.p, c->cell_rhs.p);
   c->launch_check();
   c->prof.end(id, c->stream);
-  RowOut out{c->vals.p, c->v_rhs.p, c->dinv.p, nullptr};
+  RowOut out{c->vals.p, c->v_rhs.p, c->dinv.p, c->vals_f.p};
   id = c->prof.begin(PC_ASM_ROWS, c->stream);
   if (newton)
     k_node_rows<DIM, true><<<c->n_tiles, ASM_WARPS * 32, c->tile_smem_bytes, c->stream>>>(c->M, P, c->ctx.p, c->cell_rhs.p, c->cflag.p, c->cval.p, out, c->d_tile_ptr.p);
@@ -340,8 +342,13 @@ template <int MODE>
 void spmv_vel(nsb_ctx* c, const double* x, double* y, const double* u, double* poly, PolyCoef pc) {
   size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
   const int g = nblk(c->S.nn_own, SPMV_WARPS);
-  if (c->dim == 2) k_spmv_vel<2, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, x, y, u, poly, c->dinv.p, pc);
-  else k_spmv_vel<3, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, x, y, u, poly, c->dinv.p, pc);
+  if (c->vals_f.p) {
+    if (c->dim == 2) k_spmv_vel<2, MODE, float><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals_f.p, x, y, u, poly, c->dinv.p, pc);
+    else k_spmv_vel<3, MODE, float><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals_f.p, x, y, u, poly, c->dinv.p, pc);
+  } else {
+    if (c->dim == 2) k_spmv_vel<2, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, x, y, u, poly, c->dinv.p, pc);
+    else k_spmv_vel<3, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, x, y, u, poly, c->dinv.p, pc);
+  }
   c->launch_check();
   c->prof.end(id, c->stream);
 }
@@ -903,7 +910,7 @@ int nsb_create(int dim, int device, nsb_handle* out) {
   CK(cudaMemcpyToSymbol(c_fe2, &T2, sizeof(FeTables)));
   CK(cudaMemcpyToSymbol(c_fe3, &T3, sizeof(FeTables)));
   c->opt.poly_degree_F = 32; c->opt.poly_refresh = 1; c->opt.poly_target = 0.12; c->opt.cheb_degree_Mp = 3;
-  c->opt.amg_smoother_degree = 2; c->opt.schur_mass_coeff = -1.0; c->opt.reorthogonalize = 1;
+  c->opt.amg_smoother_degree = 2; c->opt.schur_mass_coeff = -1.0; c->opt.reorthogonalize = 1; c->opt.precond_precision = 32;
   c->par.dt = 0.01; c->par.theta = 1.0; c->par.nu = 1e-3; c->par.rho = 1.0; c->par.gamma = 0.1;
   c->d_nrm.alloc(4);
   return 0;
@@ -1005,8 +1012,22 @@ int nsb_upload_mesh(nsb_handle c, int64_t n_vertices, const double* coords, int6
   c->d_pid_node.upload(pnode, st);
   c->d_pselfrank.upload(S.pselfrank, st);
   c->d_n2c.upload(S.n2c, st);
+  if (S.nbr.size() >= (size_t)INT32_MAX) return fail(c, "neighbour lists too long for 32-bit offsets");
+  std::vector<NodeDesc> nd(S.nn_own);
+  for (int A = 0; A < S.nn_own; ++A) {
+    NodeDesc& d = nd[A];
+    d.rowbase = S.rowbase[A];
+    d.pid = S.node_pid[A];
+    d.prowbase = d.pid >= 0 ? S.prowbase[d.pid] : 0;
+    d.nbr0 = (int)S.nbr_ptr[A];
+    d.pnbr0 = (int)S.pnbr_ptr[A];
+    d.nb = (unsigned short)(S.nbr_ptr[A + 1] - S.nbr_ptr[A]);
+    d.np = (unsigned short)(S.pnbr_ptr[A + 1] - S.pnbr_ptr[A]);
+  }
+  c->d_nd.upload(nd, st);
   CK(cudaStreamSynchronize(st));
   DevMesh& M = c->M;
+  M.nd = c->d_nd.p;
   M.dim = dim; M.nn_own = S.nn_own; M.nn_tot = S.nn_own + S.nn_ghost; M.np_own = S.np_own;
   M.np_tot = S.np_own + S.np_ghost; M.nc = S.nc; M.n_own = S.n_own_dofs(); M.n_tot = S.n_tot_dofs();
   M.cell_xoff = c->d_cell_xoff.p; M.cell_poff = c->d_cell_poff.p; M.cell_geom = c->d_cell_geom.p;
@@ -1026,6 +1047,7 @@ int nsb_upload_mesh(nsb_handle c, int64_t n_vertices, const double* coords, int6
   CK(cudaMallocHost(&c->pin, nt * sizeof(double)));
   c->cflag.alloc(nt); c->cflag.zero(st);
   c->vals.alloc((size_t)S.nnz_local);
+  c->vals_f.alloc(c->opt.precond_precision == 64 ? 0 : (size_t)S.nnz_local);
   c->dinv.alloc((size_t)S.nn_own * dim * dim);
   c->cell_rhs.alloc((size_t)S.nc * S.DPC);
   c->ctx_stride = 0;
@@ -1130,6 +1152,16 @@ int nsb_set_solver_opts(nsb_handle c, const nsb_solver_opts* o) {
   if (n.cheb_degree_Mp <= 0) n.cheb_degree_Mp = 3;
   if (n.amg_smoother_degree <= 0) n.amg_smoother_degree = 2;
   if (n.schur_mass_coeff == 0.0) n.schur_mass_coeff = -1.0;
+  if (n.precond_precision != 64) n.precond_precision = 32;
+  if (c->have_mesh && n.precond_precision != c->opt.precond_precision) {
+    // (de)allocate the fp32 operator copy; it is refilled by the next assembly
+    try {
+      cudaSetDevice(c->device);
+      c->vals_f.alloc(n.precond_precision == 64 ? 0 : (size_t)c->S.nnz_local);
+    } catch (const CudaErr& e) { return fail(c, e.msg); }
+    c->have_matrix = false;
+    c->poly_roots.clear();
+  }
   c->opt = n;
   return 0;
 }
