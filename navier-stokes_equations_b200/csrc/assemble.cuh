@@ -30,6 +30,16 @@ template <int DIM> __host__ __device__ constexpr int node_j(int a) {
 
 constexpr int ASM_WARPS = 8;
 
+// The FE tables are read with lane-dependent indices all over both passes; from __constant__
+// memory that serialises (one address per cycle).  Each CTA therefore keeps a copy in shared
+// memory, filled with coalesced loads from an L2-resident global copy.
+__device__ __forceinline__ void load_tables_to_smem(FeTables* dst, const FeTables* __restrict__ src) {
+  static_assert(sizeof(FeTables) % sizeof(double) == 0, "FeTables must be a whole number of 8-byte words");
+  const double* s = reinterpret_cast<const double*>(src);
+  double* d = reinterpret_cast<double*>(dst);
+  for (int i = threadIdx.x; i < (int)(sizeof(FeTables) / sizeof(double)); i += blockDim.x) d[i] = __ldg(s + i);
+}
+
 // per-quadrature-point scratch of pass 1 (shared memory, per warp)
 template <int DIM> struct QS {
   static constexpr int NV = DIM + 1;
@@ -48,18 +58,20 @@ template <int DIM> struct QS {
 // ------------------------------------------------------------------------------------
 template <int DIM, bool NEWTON>
 __global__ void __launch_bounds__(ASM_WARPS * 32)
-k_cell_context(DevMesh M, AsmParams P, const double* __restrict__ vecA, const double* __restrict__ vecB,
-               double* __restrict__ ctx_out, double* __restrict__ cell_rhs) {
+k_cell_context(DevMesh M, AsmParams P, const FeTables* __restrict__ gT, const double* __restrict__ vecA,
+               const double* __restrict__ vecB, double* __restrict__ ctx_out, double* __restrict__ cell_rhs) {
   constexpr int NV = DIM + 1, NN = Fe<DIM>::NN, NQ = Fe<DIM>::NQ, DPC = Fe<DIM>::DPC;
   using C = Ctx<DIM>;
   using Q = QS<DIM>;
   constexpr int CTXN = NEWTON ? C::N_NEWTON : C::N_LIN;
   constexpr int WS = NN * DIM * 2 + NV + 4 + NQ * Q::N;     // doubles per warp
   __shared__ double sm_all[ASM_WARPS * WS];
-  const FeTables& T = fe_tab<DIM>();
+  __shared__ FeTables sT;
+  load_tables_to_smem(&sT, gT);
+  __syncthreads();
+  const FeTables& T = sT;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int cell = blockIdx.x * ASM_WARPS + wid;
-  if (cell >= M.nc) return;
+  for (int cell = blockIdx.x * ASM_WARPS + wid; cell < M.nc; cell += gridDim.x * ASM_WARPS) {
   double* su = sm_all + wid * WS;          // vecA velocity [NN][DIM]
   double* sv = su + NN * DIM;              // vecB velocity [NN][DIM]
   double* sp = sv + NN * DIM;              // vecA pressure [NV]
@@ -264,6 +276,8 @@ k_cell_context(DevMesh M, AsmParams P, const double* __restrict__ vecA, const do
   if (lane < NQ) co[C::TW + lane] = sq[lane * Q::N + Q::TW];
   if (NEWTON)
     for (int k = lane; k < NQ * DIM * DIM; k += 32) co[C::H + k] = sq[(k / (DIM * DIM)) * Q::N + Q::HH + (k % (DIM * DIM))];
+  __syncwarp();
+  }   // cell loop
 }
 
 // ------------------------------------------------------------------------------------
@@ -280,7 +294,7 @@ template <int DIM, bool NEWTON>
 __global__ void __launch_bounds__(ASM_WARPS * 32)
 k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double* __restrict__ cell_rhs,
             const unsigned char* __restrict__ cflag, const double* __restrict__ cval, RowOut out,
-            const int* __restrict__ tile_ptr) {
+            const int* __restrict__ tile_ptr, const FeTables* __restrict__ gT) {
   constexpr int NV = DIM + 1, NN = Fe<DIM>::NN, NQ = Fe<DIM>::NQ, DPC = Fe<DIM>::DPC;
   using C = Ctx<DIM>;
   constexpr int CTXN = NEWTON ? C::N_NEWTON : C::N_LIN;
@@ -289,7 +303,9 @@ k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double
   __shared__ double s_ctx[ASM_WARPS][CTXN];
   __shared__ int s_next;
   __shared__ int s_off[65];
-  const FeTables& T = fe_tab<DIM>();
+  __shared__ FeTables sT;
+  load_tables_to_smem(&sT, gT);
+  const FeTables& T = sT;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int n0 = tile_ptr[blockIdx.x], n1 = tile_ptr[blockIdx.x + 1];
   // shared-memory offsets of the tile's nodes (tile has at most 64 nodes)

@@ -53,13 +53,6 @@ struct AsmParams {
   int first_order_ustar;                // first_step || second_step || BackwardEuler (cpp:665)
 };
 
-__constant__ FeTables c_fe2;            // dim == 2 tables
-__constant__ FeTables c_fe3;            // dim == 3 tables
-
-template <int DIM> __device__ __forceinline__ const FeTables& fe_tab() {
-  if (DIM == 2) return c_fe2;
-  return c_fe3;
-}
 
 // Context written per cell by the first pass and consumed by the node-row pass.
 template <int DIM> struct Ctx {

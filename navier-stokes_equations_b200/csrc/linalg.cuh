@@ -52,7 +52,7 @@ __device__ __forceinline__ void row_block_dot(const VT* const (&rowp)[ROWS], int
 #pragma unroll
       for (int r = 0; r < ROWS; ++r) v[r][u] = ok ? __ldcs(rowp[r] + k) : VT(0);
       xo[u] = -1;
-      if (ok) xo[u] = (k < nbd) ? (__ldg(nx + k / DIM) + k % DIM) : __ldg(px + (k - nbd));
+      if (ok) xo[u] = (k < nbd) ? (nx[k / DIM] + k % DIM) : px[k - nbd];
     }
 #pragma unroll
     for (int u = 0; u < SPMV_UNROLL; ++u) xv[u] = xo[u] >= 0 ? __ldg(x + xo[u]) : 0.0;
@@ -63,17 +63,73 @@ __device__ __forceinline__ void row_block_dot(const VT* const (&rowp)[ROWS], int
   }
 }
 
+// A tile = a run of consecutive owned nodes whose descriptors and neighbour-offset lists fit the
+// CTA's shared memory.  The CTA first stages them with fully coalesced loads (two dependent
+// latencies per TILE instead of per node), then its warps pull nodes off a shared counter and
+// only stream matrix values and gather x.
+constexpr int TILE_MAX_NODES = 64;
+constexpr int TILE_MAX_IDX = 4096;
+
+struct TileSmem {
+  int4 desc[TILE_MAX_NODES * 2];
+  int idx[TILE_MAX_IDX];
+  int next, base_n, cnt_n, base_p;
+};
+
+template <bool WITH_P>
+__device__ __forceinline__ void stage_tile(const DevMesh& M, int n0, int n1, TileSmem& T) {
+  const int nn = n1 - n0;
+  const int4* g = reinterpret_cast<const int4*>(M.nd + n0);
+  for (int i = threadIdx.x; i < 2 * nn; i += blockDim.x) T.desc[i] = __ldg(g + i);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int4 f = T.desc[1], l = T.desc[2 * nn - 1];
+    T.base_n = f.x;
+    T.cnt_n = l.x + (l.z & 0xffff) - f.x;
+    T.base_p = f.y;
+    T.next = 0;
+  }
+  __syncthreads();
+  const int base_n = T.base_n, cnt_n = T.cnt_n;
+  for (int i = threadIdx.x; i < cnt_n; i += blockDim.x) T.idx[i] = __ldg(M.nbr_xoff + base_n + i);
+  if (WITH_P) {
+    const int4 l = T.desc[2 * nn - 1];
+    const int cnt_p = l.y + (int)((unsigned)l.z >> 16) - T.base_p;
+    for (int i = threadIdx.x; i < cnt_p; i += blockDim.x) T.idx[cnt_n + i] = __ldg(M.pnbr_xoff + T.base_p + i);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ NodeDesc desc_from_smem(const TileSmem& T, int slot) {
+  const int4 a = T.desc[2 * slot], b = T.desc[2 * slot + 1];
+  NodeDesc d;
+  d.rowbase = ((long long)(unsigned)a.y << 32) | (unsigned)a.x;
+  d.prowbase = ((long long)(unsigned)a.w << 32) | (unsigned)a.z;
+  d.nbr0 = b.x; d.pnbr0 = b.y;
+  d.nb = (unsigned short)(b.z & 0xffff); d.np = (unsigned short)((unsigned)b.z >> 16);
+  d.pid = b.w;
+  return d;
+}
+
 // y = A x
 template <int DIM, typename VT>
 __global__ void __launch_bounds__(SPMV_WARPS * 32)
-k_spmv_full(DevMesh M, const VT* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y) {
+k_spmv_full(DevMesh M, const int* __restrict__ tile_ptr, const VT* __restrict__ vals, const double* __restrict__ x,
+            double* __restrict__ y) {
+  __shared__ TileSmem T;
   const int lane = threadIdx.x & 31;
-  const int A = blockIdx.x * SPMV_WARPS + (threadIdx.x >> 5);
-  if (A >= M.nn_own) return;
-  const NodeDesc d = load_desc(M.nd + A);
+  const int n0 = tile_ptr[blockIdx.x], n1 = tile_ptr[blockIdx.x + 1];
+  stage_tile<true>(M, n0, n1, T);
+  for (;;) {
+  int slot = 0;
+  if (lane == 0) slot = atomicAdd(&T.next, 1);
+  slot = __shfl_sync(NSB_FULL, slot, 0);
+  const int A = n0 + slot;
+  if (A >= n1) break;
+  const NodeDesc d = desc_from_smem(T, slot);
   const int nbd = DIM * d.nb, len = nbd + d.np;
-  const int* nx = M.nbr_xoff + d.nbr0;
-  const int* px = M.pnbr_xoff + d.pnbr0;
+  const int* nx = T.idx + (d.nbr0 - T.base_n);
+  const int* px = T.idx + T.cnt_n + (d.pnbr0 - T.base_p);
   if (d.pid >= 0) {
     const VT* rowp[DIM + 1];
 #pragma unroll
@@ -109,6 +165,7 @@ k_spmv_full(DevMesh M, const VT* __restrict__ vals, const double* __restrict__ x
       y[DIM * A + lane] = v;
     }
   }
+  }   // node loop
 }
 
 // ------------------------------------------------------------------------------------
@@ -126,12 +183,20 @@ struct PolyCoef {
 
 template <int DIM, int MODE, typename VT>
 __global__ void __launch_bounds__(SPMV_WARPS * 32)
-k_spmv_vel(DevMesh M, const VT* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
-           const double* __restrict__ u, double* __restrict__ poly, const double* __restrict__ dinv, PolyCoef pc) {
+k_spmv_vel(DevMesh M, const int* __restrict__ tile_ptr, const VT* __restrict__ vals, const double* __restrict__ x,
+           double* __restrict__ y, const double* __restrict__ u, double* __restrict__ poly,
+           const double* __restrict__ dinv, PolyCoef pc) {
+  __shared__ TileSmem T;
   const int lane = threadIdx.x & 31;
-  const int A = blockIdx.x * SPMV_WARPS + (threadIdx.x >> 5);
-  if (A >= M.nn_own) return;
-  const NodeDesc d = load_desc(M.nd + A);
+  const int n0 = tile_ptr[blockIdx.x], n1 = tile_ptr[blockIdx.x + 1];
+  stage_tile<false>(M, n0, n1, T);
+  for (;;) {
+  int slot = 0;
+  if (lane == 0) slot = atomicAdd(&T.next, 1);
+  slot = __shfl_sync(NSB_FULL, slot, 0);
+  const int A = n0 + slot;
+  if (A >= n1) break;
+  const NodeDesc d = desc_from_smem(T, slot);
   const int nbd = DIM * d.nb, len = nbd + d.np;
   const VT* rowp[DIM];
 #pragma unroll
@@ -139,7 +204,7 @@ k_spmv_vel(DevMesh M, const VT* __restrict__ vals, const double* __restrict__ x,
   double sum[DIM];
 #pragma unroll
   for (int c = 0; c < DIM; ++c) sum[c] = 0.0;
-  row_block_dot<DIM, DIM, VT>(rowp, nbd, nbd, M.nbr_xoff + d.nbr0, nullptr, x, lane, sum);
+  row_block_dot<DIM, DIM, VT>(rowp, nbd, nbd, T.idx + (d.nbr0 - T.base_n), nullptr, x, lane, sum);
 #pragma unroll
   for (int c = 0; c < DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
   if (lane < DIM) {
@@ -163,6 +228,7 @@ k_spmv_vel(DevMesh M, const VT* __restrict__ vals, const double* __restrict__ x,
       }
     }
   }
+  }   // node loop
 }
 
 // t = g - B y0 : pressure rows, velocity columns (reference NavierStokes.hpp:334-335)

@@ -187,7 +187,11 @@ struct nsb_ctx {
   DBuf<long long> d_nbr_ptr, d_pnbr_ptr, d_rowbase, d_prowbase, d_n2c_ptr;
   DBuf<uint32_t> d_n2c;
   DBuf<NodeDesc> d_nd;
+  DBuf<FeTables> d_fe;              // L2-resident copy of the FE tables (kernels stage it in shared memory)
+  int num_sms = 148;
   int n_tiles = 0, tile_smem_bytes = 0;
+  DBuf<int> d_stile_ptr;            // SpMV tiles (descriptor + index staging in shared memory)
+  int n_stiles = 0;
   // global dof -> local vector offset (or -1)
   std::vector<int> g2x;
   DBuf<int> d_own_gather;           // unused on device; host maps instead
@@ -308,18 +312,19 @@ template <int DIM> void launch_assemble(nsb_ctx* c, bool newton) {
   const double* vecA = newton ? c->v_cur.p : c->v_old.p;
   const double* vecB = newton ? c->v_old.p : c->v_oldold.p;
   size_t id = c->prof.begin(PC_ASM_CTX, c->stream);
+  const int cgrid = std::min(nblk(c->S.nc, ASM_WARPS), c->num_sms * 8);     // persistent: CTAs stride over the cells
   if (newton)
-    k_cell_context<DIM, true><<<nblk(c->S.nc, ASM_WARPS), ASM_WARPS * 32, 0, c->stream>>>(c->M, P, vecA, vecB, c->ctx.p, c->cell_rhs.p);
+    k_cell_context<DIM, true><<<cgrid, ASM_WARPS * 32, 0, c->stream>>>(c->M, P, c->d_fe.p, vecA, vecB, c->ctx.p, c->cell_rhs.p);
   else
-    k_cell_context<DIM, false><<<nblk(c->S.nc, ASM_WARPS), ASM_WARPS * 32, 0, c->stream>>>(c->M, P, vecA, vecB, c->ctx.p, c->cell_rhs.p);
+    k_cell_context<DIM, false><<<cgrid, ASM_WARPS * 32, 0, c->stream>>>(c->M, P, c->d_fe.p, vecA, vecB, c->ctx.p, c->cell_rhs.p);
   c->launch_check();
   c->prof.end(id, c->stream);
   RowOut out{c->vals.p, c->v_rhs.p, c->dinv.p, c->vals_f.p};
   id = c->prof.begin(PC_ASM_ROWS, c->stream);
   if (newton)
-    k_node_rows<DIM, true><<<c->n_tiles, ASM_WARPS * 32, c->tile_smem_bytes, c->stream>>>(c->M, P, c->ctx.p, c->cell_rhs.p, c->cflag.p, c->cval.p, out, c->d_tile_ptr.p);
+    k_node_rows<DIM, true><<<c->n_tiles, ASM_WARPS * 32, c->tile_smem_bytes, c->stream>>>(c->M, P, c->ctx.p, c->cell_rhs.p, c->cflag.p, c->cval.p, out, c->d_tile_ptr.p, c->d_fe.p);
   else
-    k_node_rows<DIM, false><<<c->n_tiles, ASM_WARPS * 32, c->tile_smem_bytes, c->stream>>>(c->M, P, c->ctx.p, c->cell_rhs.p, c->cflag.p, c->cval.p, out, c->d_tile_ptr.p);
+    k_node_rows<DIM, false><<<c->n_tiles, ASM_WARPS * 32, c->tile_smem_bytes, c->stream>>>(c->M, P, c->ctx.p, c->cell_rhs.p, c->cflag.p, c->cval.p, out, c->d_tile_ptr.p, c->d_fe.p);
   c->launch_check();
   c->prof.end(id, c->stream);
 }
@@ -332,8 +337,8 @@ template <int DIM> void set_smem_attr(int bytes) {
 // y(owned) = A x ; x must have a valid ghost tail
 void spmv_full(nsb_ctx* c, const double* x, double* y) {
   size_t id = c->prof.begin(PC_SPMV, c->stream);
-  if (c->dim == 2) k_spmv_full<2, double><<<nblk(c->S.nn_own, SPMV_WARPS), SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, x, y);
-  else k_spmv_full<3, double><<<nblk(c->S.nn_own, SPMV_WARPS), SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, x, y);
+  if (c->dim == 2) k_spmv_full<2, double><<<c->n_stiles, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, c->vals.p, x, y);
+  else k_spmv_full<3, double><<<c->n_stiles, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, c->vals.p, x, y);
   c->launch_check();
   c->prof.end(id, c->stream);
 }
@@ -341,13 +346,13 @@ void spmv_full(nsb_ctx* c, const double* x, double* y) {
 template <int MODE>
 void spmv_vel(nsb_ctx* c, const double* x, double* y, const double* u, double* poly, PolyCoef pc) {
   size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
-  const int g = nblk(c->S.nn_own, SPMV_WARPS);
+  const int g = c->n_stiles;
   if (c->vals_f.p) {
-    if (c->dim == 2) k_spmv_vel<2, MODE, float><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals_f.p, x, y, u, poly, c->dinv.p, pc);
-    else k_spmv_vel<3, MODE, float><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals_f.p, x, y, u, poly, c->dinv.p, pc);
+    if (c->dim == 2) k_spmv_vel<2, MODE, float><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, c->vals_f.p, x, y, u, poly, c->dinv.p, pc);
+    else k_spmv_vel<3, MODE, float><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, c->vals_f.p, x, y, u, poly, c->dinv.p, pc);
   } else {
-    if (c->dim == 2) k_spmv_vel<2, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, x, y, u, poly, c->dinv.p, pc);
-    else k_spmv_vel<3, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->vals.p, x, y, u, poly, c->dinv.p, pc);
+    if (c->dim == 2) k_spmv_vel<2, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, c->vals.p, x, y, u, poly, c->dinv.p, pc);
+    else k_spmv_vel<3, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, c->vals.p, x, y, u, poly, c->dinv.p, pc);
   }
   c->launch_check();
   c->prof.end(id, c->stream);
@@ -771,7 +776,7 @@ void build_tiles(nsb_ctx* c) {
   const Structure& S = c->S;
   int dev_max = 0;
   CK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-  const int stat = 16 * 1024;      // static shared memory of k_node_rows (upper bound)
+  const int stat = 24 * 1024;      // static shared memory of k_node_rows (upper bound: context staging + FE tables)
   int budget = std::max(S.max_node_smem_doubles, 5 * 1024);      // doubles: >= 40 KB
   if ((long long)budget * 8 + stat > dev_max)
     throw CudaErr{"a node's rows do not fit in shared memory (valence too high)"};
@@ -787,6 +792,20 @@ void build_tiles(nsb_ctx* c) {
   c->n_tiles = (int)tp.size() - 1;
   c->tile_smem_bytes = budget * 8;
   c->d_tile_ptr.upload(tp, c->stream);
+  // SpMV tiles: at most TILE_MAX_NODES nodes and TILE_MAX_IDX staged neighbour offsets
+  std::vector<int> sp;
+  sp.push_back(0);
+  int idx = 0, cn = 0;
+  for (int A = 0; A < S.nn_own; ++A) {
+    const int need = (int)(S.nbr_ptr[A + 1] - S.nbr_ptr[A]) + (int)(S.pnbr_ptr[A + 1] - S.pnbr_ptr[A]);
+    if (need > TILE_MAX_IDX) throw CudaErr{"a node has more neighbours than one SpMV tile can stage"};
+    if (cn > 0 && (idx + need > TILE_MAX_IDX || cn >= TILE_MAX_NODES)) { sp.push_back(A); idx = 0; cn = 0; }
+    idx += need; ++cn;
+  }
+  sp.push_back(S.nn_own);
+  c->n_stiles = (int)sp.size() - 1;
+  c->d_stile_ptr.upload(sp, c->stream);
+  CK(cudaStreamSynchronize(c->stream));
   if (c->dim == 2) set_smem_attr<2>(c->tile_smem_bytes);
   else set_smem_attr<3>(c->tile_smem_bytes);
 }
@@ -907,8 +926,12 @@ int nsb_create(int dim, int device, nsb_handle* out) {
   FeTables T2, T3;
   fill_tables(2, T2);
   fill_tables(3, T3);
-  CK(cudaMemcpyToSymbol(c_fe2, &T2, sizeof(FeTables)));
-  CK(cudaMemcpyToSymbol(c_fe3, &T3, sizeof(FeTables)));
+  {
+    std::vector<FeTables> tv(1, dim == 2 ? T2 : T3);
+    c->d_fe.upload(tv, c->stream);
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   c->opt.poly_degree_F = 32; c->opt.poly_refresh = 1; c->opt.poly_target = 0.12; c->opt.cheb_degree_Mp = 3;
   c->opt.amg_smoother_degree = 2; c->opt.schur_mass_coeff = -1.0; c->opt.reorthogonalize = 1; c->opt.precond_precision = 32;
   c->par.dt = 0.01; c->par.theta = 1.0; c->par.nu = 1e-3; c->par.rho = 1.0; c->par.gamma = 0.1;
