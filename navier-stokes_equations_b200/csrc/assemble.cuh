@@ -287,7 +287,7 @@ struct RowOut {
   double* vals;            // CSR values of A (local rows, scalar-CSR order)
   double* rhs;             // [n_own]
   double* dinv;            // [nn_own][DIM*DIM]  inverse of the node-diagonal velocity block (preconditioner)
-  float* vals_f;           // optional fp32 copy of the values (preconditioner operator), may be null
+  float* vals_f;           // optional fp32 copy of F, node-interleaved (see k_spmv_vel_f32), may be null
 };
 
 template <int DIM, bool NEWTON>
@@ -492,14 +492,19 @@ k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double
         if (crow[c]) v = (k == selfk + c) ? dacc[c] : 0.0;
         acc[c * len + k] = v;
         out.vals[M.rowbase[A] + (long long)c * len + k] = v;
-        if (out.vals_f) out.vals_f[M.rowbase[A] + (long long)c * len + k] = (float)v;
+      }
+      if (out.vals_f && k < DIM * nb) {
+        // fp32 copy of the velocity block, one vector per column holding all DIM rows
+        constexpr int W = (DIM == 3) ? 4 : 2;
+        float* o = out.vals_f + ((long long)DIM * nptr[0] + k) * W;
+        if (DIM == 3) *reinterpret_cast<float4*>(o) = make_float4((float)acc[k], (float)acc[len + k], (float)acc[2 * len + k], 0.f);
+        else *reinterpret_cast<float2*>(o) = make_float2((float)acc[k], (float)acc[len + k]);
       }
       if (isv) {
         double v = acc[DIM * len + k];
         if (ccol) { corr[DIM] += v * g; v = 0.0; }
         if (crow[DIM]) v = (k == DIM * nb + M.pselfrank[pid]) ? dacc[DIM] : 0.0;
         out.vals[M.prowbase[pid] + k] = v;
-        if (out.vals_f) out.vals_f[M.prowbase[pid] + k] = (float)v;
       }
     }
 #pragma unroll

@@ -231,6 +231,77 @@ k_spmv_vel(DevMesh M, const int* __restrict__ tile_ptr, const VT* __restrict__ v
   }   // node loop
 }
 
+// Same operator and epilogues as k_spmv_vel, reading the PRIVATE fp32 copy of F that the assembly
+// writes node-interleaved: for node A and column k < dim*nb one vector {F[(A,0),k], .., F[(A,dim-1),k](,0)}
+// at index dim*nbr0(A) + k.  One 16-byte (3-D) / 8-byte (2-D) load per lane and column delivers all rows,
+// three times fewer memory requests than the row-major fp64 layout and 2/3 of its bytes.  Products are
+// accumulated in fp64, so the preconditioner remains a fixed linear operator.
+template <int DIM> struct F32Vec { using type = float4; };
+template <> struct F32Vec<2> { using type = float2; };
+
+template <int DIM, int MODE>
+__global__ void __launch_bounds__(SPMV_WARPS * 32)
+k_spmv_vel_f32(DevMesh M, const int* __restrict__ tile_ptr, const typename F32Vec<DIM>::type* __restrict__ fv,
+               const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ u,
+               double* __restrict__ poly, const double* __restrict__ dinv, PolyCoef pc) {
+  using V = typename F32Vec<DIM>::type;
+  __shared__ TileSmem T;
+  const int lane = threadIdx.x & 31;
+  const int n0 = tile_ptr[blockIdx.x], n1 = tile_ptr[blockIdx.x + 1];
+  stage_tile<false>(M, n0, n1, T);
+  for (;;) {
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(&T.next, 1);
+    slot = __shfl_sync(NSB_FULL, slot, 0);
+    const int A = n0 + slot;
+    if (A >= n1) break;
+    const NodeDesc d = desc_from_smem(T, slot);
+    const int nbd = DIM * d.nb;
+    const V* rp = fv + (long long)DIM * d.nbr0;
+    const int* nx = T.idx + (d.nbr0 - T.base_n);
+    double sum[DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) sum[c] = 0.0;
+    for (int k0 = 0; k0 < nbd; k0 += 32 * SPMV_UNROLL) {
+      V v[SPMV_UNROLL];
+      int xo[SPMV_UNROLL];
+      double xv[SPMV_UNROLL];
+#pragma unroll
+      for (int q = 0; q < SPMV_UNROLL; ++q) {
+        const int k = k0 + 32 * q + lane;
+        const bool ok = k < nbd;
+        v[q] = V();
+        xo[q] = -1;
+        if (ok) { v[q] = __ldcs(rp + k); xo[q] = nx[k / DIM] + k % DIM; }
+      }
+#pragma unroll
+      for (int q = 0; q < SPMV_UNROLL; ++q) xv[q] = xo[q] >= 0 ? __ldg(x + xo[q]) : 0.0;
+#pragma unroll
+      for (int q = 0; q < SPMV_UNROLL; ++q) {
+        sum[0] += (double)v[q].x * xv[q];
+        sum[1] += (double)v[q].y * xv[q];
+        if (DIM == 3) sum[DIM - 1] += (double)reinterpret_cast<const float*>(&v[q])[DIM - 1] * xv[q];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
+    if (lane < DIM) {
+      const int row = DIM * A + lane;
+      double t = 0.0;
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) t += dinv[(size_t)A * DIM * DIM + lane * DIM + c] * sum[c];
+      if (MODE == 2) {
+        y[row] = t;
+      } else {
+        const double uv = u[row];
+        const double yv = pc.cu * uv + pc.ct * t;
+        y[row] = yv;
+        poly[row] += pc.cpu * uv + pc.cpy * yv;
+      }
+    }
+  }
+}
+
 // t = g - B y0 : pressure rows, velocity columns (reference NavierStokes.hpp:334-335)
 template <int DIM, typename VT>
 __global__ void __launch_bounds__(SPMV_WARPS * 32)

@@ -347,9 +347,9 @@ template <int MODE>
 void spmv_vel(nsb_ctx* c, const double* x, double* y, const double* u, double* poly, PolyCoef pc) {
   size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
   const int g = c->n_stiles;
-  if (c->vals_f.p) {
-    if (c->dim == 2) k_spmv_vel<2, MODE, float><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, c->vals_f.p, x, y, u, poly, c->dinv.p, pc);
-    else k_spmv_vel<3, MODE, float><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, c->vals_f.p, x, y, u, poly, c->dinv.p, pc);
+  if (c->vals_f.p && MODE != 0) {
+    if (c->dim == 2) k_spmv_vel_f32<2, MODE><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, reinterpret_cast<const float2*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
+    else k_spmv_vel_f32<3, MODE><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, reinterpret_cast<const float4*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
   } else {
     if (c->dim == 2) k_spmv_vel<2, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, c->vals.p, x, y, u, poly, c->dinv.p, pc);
     else k_spmv_vel<3, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, c->vals.p, x, y, u, poly, c->dinv.p, pc);
@@ -1070,7 +1070,7 @@ int nsb_upload_mesh(nsb_handle c, int64_t n_vertices, const double* coords, int6
   CK(cudaMallocHost(&c->pin, nt * sizeof(double)));
   c->cflag.alloc(nt); c->cflag.zero(st);
   c->vals.alloc((size_t)S.nnz_local);
-  c->vals_f.alloc(c->opt.precond_precision == 64 ? 0 : (size_t)S.nnz_local);
+  c->vals_f.alloc(c->opt.precond_precision == 64 ? 0 : (size_t)S.nbr.size() * dim * (dim == 3 ? 4 : 2));
   c->dinv.alloc((size_t)S.nn_own * dim * dim);
   c->cell_rhs.alloc((size_t)S.nc * S.DPC);
   c->ctx_stride = 0;
@@ -1180,7 +1180,7 @@ int nsb_set_solver_opts(nsb_handle c, const nsb_solver_opts* o) {
     // (de)allocate the fp32 operator copy; it is refilled by the next assembly
     try {
       cudaSetDevice(c->device);
-      c->vals_f.alloc(n.precond_precision == 64 ? 0 : (size_t)c->S.nnz_local);
+      c->vals_f.alloc(n.precond_precision == 64 ? 0 : (size_t)c->S.nbr.size() * c->dim * (c->dim == 3 ? 4 : 2));
     } catch (const CudaErr& e) { return fail(c, e.msg); }
     c->have_matrix = false;
     c->poly_roots.clear();
