@@ -100,7 +100,8 @@ enum {
 /* v has the GLOBAL length n_u+n_p; every rank passes the full vector (ghost import,
  * cpp:1053-1056,1299-1300). */
 int nsb_set_vector(nsb_handle h, int which, const double* v_global);
-/* writes the owned entries at their global indices; other entries are left untouched */
+/* full vector in global numbering.  With more than one rank this is a COLLECTIVE call: every rank
+ * receives the whole vector (what the reference gets from its ghosted vectors + MPI). */
 int nsb_get_vector(nsb_handle h, int which, double* v_global);
 /* device-resident time-level bookkeeping of run() (cpp:1299-1300, 1183-1185):
  * dst = src ;  dst += alpha * src.  Ghost entries are refreshed. */

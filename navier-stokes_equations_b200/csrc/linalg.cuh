@@ -518,6 +518,13 @@ __global__ void k_lincomb(long long n, double a, const double* __restrict__ x, d
   if (i < n) y[i] = a * x[i] + b * z[i];
 }
 
+// out[i] = a * x[idx[i]] + b * z[idx[i]]   (owned pressure entries out of replicated global vectors)
+__global__ void k_lincomb_gather(int n, const int* __restrict__ idx, double a, const double* __restrict__ x, double b,
+                                 const double* __restrict__ z, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const int g = idx[i]; out[i] = a * x[g] + b * z[g]; }
+}
+
 // scatter constraint values / flags;  x[dof] = val  (constraints.distribute, reference cpp:566, 862)
 __global__ void k_scatter_vals(int n, const int* __restrict__ idx, const double* __restrict__ val, double* __restrict__ x) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

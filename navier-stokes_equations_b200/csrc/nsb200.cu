@@ -194,7 +194,9 @@ struct nsb_ctx {
   int n_stiles = 0;
   // global dof -> local vector offset (or -1)
   std::vector<int> g2x;
-  DBuf<int> d_own_gather;           // unused on device; host maps instead
+  DBuf<int> d_pid_gid;              // [np_own] global pressure id of each owned pressure DoF (multi-GPU)
+  DBuf<int> d_own_gdof;             // [n_own] global DoF of each owned local entry (multi-GPU gathers)
+  DBuf<double> w_tg, w_gather;      // replicated global pressure vector / full global vector
   // vectors, all in local layout [u_own | p_own | u_ghost | p_ghost]
   DBuf<double> v_old, v_oldold, v_cur, v_sol, v_rhs;
   DBuf<unsigned char> cflag;
@@ -643,6 +645,15 @@ void precond_apply(nsb_ctx* c, const double* x, double* y) {
   c->prof.end(id, c->stream);
   // --- step 3: Cahouet-Chabard Schur complement on the (replicated) pressure space
   const double* tg = c->w_t.p;     // one rank: local pressure ids == global ids
+  if (c->nranks > 1) {
+    // replicate the pressure-space vector: zero-padded all-reduce of the owned entries (exact: one
+    // non-zero summand per entry), so every GPU applies the same global multigrid cycle
+    CK(cudaMemsetAsync(c->w_tg.p, 0, (size_t)c->n_p * sizeof(double), c->stream));
+    k_scatter_vals<<<nblk(S.np_own, 256), 256, 0, c->stream>>>(S.np_own, c->d_pid_gid.p, c->w_t.p, c->w_tg.p);
+    c->launch_check();
+    allreduce_sum(c, c->w_tg.p, (int)c->n_p);
+    tg = c->w_tg.p;
+  }
   id = c->prof.begin(PC_AMG, c->stream);
   DevLevel& L0 = *c->amg[0];
   CK(cudaMemcpyAsync(L0.b.p, tg, (size_t)L0.n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -651,7 +662,10 @@ void precond_apply(nsb_ctx* c, const double* x, double* y) {
   csr_cheb(c, c->Mp, c->Mp_dinv.p, c->Mp_lmax, 6.0, c->opt.cheb_degree_Mp, tg, c->w_m0.p, c->w_m1.p, c->w_md.p, true, &mres);
   double cm = c->opt.schur_mass_coeff;
   if (cm < 0) cm = c->par.theta * c->par.nu + (c->par.use_supg ? c->par.gamma : 0.0);
-  k_lincomb<<<nblk(S.np_own, 256), 256, 0, c->stream>>>(S.np_own, -(c->par.rho / c->par.dt), L0.x.p, -cm, mres, y + nu);
+  if (c->nranks > 1)
+    k_lincomb_gather<<<nblk(S.np_own, 256), 256, 0, c->stream>>>(S.np_own, c->d_pid_gid.p, -(c->par.rho / c->par.dt), L0.x.p, -cm, mres, y + nu);
+  else
+    k_lincomb<<<nblk(S.np_own, 256), 256, 0, c->stream>>>(S.np_own, -(c->par.rho / c->par.dt), L0.x.p, -cm, mres, y + nu);
   c->launch_check();
   c->prof.end(id, c->stream);
 }
@@ -1059,6 +1073,18 @@ int nsb_upload_mesh(nsb_handle c, int64_t n_vertices, const double* coords, int6
   M.selfrank = c->d_selfrank.p; M.node_pid = c->d_node_pid.p; M.pid_node = c->d_pid_node.p; M.pselfrank = c->d_pselfrank.p;
   M.rowbase = c->d_rowbase.p; M.prowbase = c->d_prowbase.p; M.n2c_ptr = c->d_n2c_ptr.p; M.n2c = c->d_n2c.p;
   build_tiles(c);
+  if (c->nranks > 1) {
+    std::vector<int> pg(S.np_own), og(S.n_own_dofs());
+    for (int P = 0; P < S.np_own; ++P) pg[P] = (int)S.pid_gid[P];
+    for (int A = 0; A < S.nn_own; ++A)
+      for (int k = 0; k < dim; ++k) og[(size_t)dim * A + k] = (int)(S.node_gid[A] * dim + k);
+    for (int P = 0; P < S.np_own; ++P) og[(size_t)dim * S.nn_own + P] = (int)(n_u + S.pid_gid[P]);
+    c->d_pid_gid.upload(pg, st);
+    c->d_own_gdof.upload(og, st);
+    c->w_tg.alloc((size_t)n_p);
+    c->w_gather.alloc((size_t)(n_u + n_p));
+    CK(cudaStreamSynchronize(st));
+  }
   // vectors and system storage
   const size_t nt = (size_t)S.n_tot_dofs();
   for (DBuf<double>* v : {&c->v_old, &c->v_oldold, &c->v_cur, &c->v_sol, &c->v_rhs, &c->cval, &c->w_z0, &c->w_z1, &c->w_d,
@@ -1220,16 +1246,21 @@ int nsb_get_vector(nsb_handle c, int which, double* vg) {
   double* d = vec_ptr(c, which);
   if (!d) return fail(c, "bad vector id");
   const Structure& S = c->S;
-  double* loc = c->pin;
-  CK(cudaMemcpyAsync(loc, d, (size_t)S.n_own_dofs() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  const int dim = c->dim;
   if (c->nranks == 1) {
-    std::memcpy(vg, loc, (size_t)S.n_own_dofs() * sizeof(double));
+    CK(cudaMemcpyAsync(c->pin, d, (size_t)S.n_own_dofs() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::memcpy(vg, c->pin, (size_t)S.n_own_dofs() * sizeof(double));
   } else {
-    for (int A = 0; A < S.nn_own; ++A)
-      for (int k = 0; k < dim; ++k) vg[S.node_gid[A] * dim + k] = loc[(size_t)dim * A + k];
-    for (int P = 0; P < S.np_own; ++P) vg[c->n_u + S.pid_gid[P]] = loc[(size_t)dim * S.nn_own + P];
+    // collective: every rank receives the full vector (owned entries scattered to their global
+    // positions, zero elsewhere, summed over the ranks)
+    const size_t N = (size_t)(c->n_u + c->n_p);
+    CK(cudaMemsetAsync(c->w_gather.p, 0, N * sizeof(double), c->stream));
+    const int n = (int)S.n_own_dofs();
+    k_scatter_vals<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->d_own_gdof.p, d, c->w_gather.p);
+    c->launch_check();
+    CKN(g_nccl.AllReduce(c->w_gather.p, c->w_gather.p, N, ncclDouble, ncclSum, c->comm, c->stream));
+    CK(cudaMemcpyAsync(vg, c->w_gather.p, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
   }
   return 0;
   NSB_CATCH(c)
@@ -1349,7 +1380,6 @@ int nsb_rhs_norm(nsb_handle c, double* norm) {
 int nsb_solve(nsb_handle c, int max_it, double tol_rel, int n_tmp, int* iterations, double* residual) {
   if (!c || !c->have_matrix) return fail(c, "no assembled system");
   if (!c->have_pressure) return fail(c, "nsb_assemble_pressure_matrices has not been called");
-  if (c->nranks > 1) return fail(c, "multi-GPU Schur-complement gather is not wired yet");
   NSB_TRY
   CK(cudaSetDevice(c->device));
   int it = 0;
