@@ -63,44 +63,72 @@ __device__ __forceinline__ void row_block_dot(const VT* const (&rowp)[ROWS], int
   }
 }
 
-// A tile = a run of consecutive owned nodes whose descriptors and neighbour-offset lists fit the
-// CTA's shared memory.  The CTA first stages them with fully coalesced loads (two dependent
-// latencies per TILE instead of per node), then its warps pull nodes off a shared counter and
-// only stream matrix values and gather x.
+// A tile = a run of consecutive owned nodes.  The host precomputes, per tile, the UNIQUE
+// neighbour nodes / pressure DoFs it touches and rewrites every neighbour reference as a 16-bit
+// position in that list.  The CTA stages descriptors, those positions and the x-values of the
+// unique neighbours in shared memory with coalesced loads (each x entry is read once per tile
+// instead of once per row that references it), then its warps pull nodes off a shared counter
+// and only stream matrix values; the x "gather" happens in shared memory.  This is what takes
+// the scattered 8-byte gathers -- which saturated L1/TEX at ~12 wavefronts per request -- out
+// of the inner loop.
 constexpr int TILE_MAX_NODES = 64;
-constexpr int TILE_MAX_IDX = 4096;
+constexpr int TILE_MAX_IDX = 3072;       // staged 16-bit neighbour positions (velocity + pressure)
+constexpr int TILE_MAX_UNIQ = 768;       // unique neighbour nodes per tile
+constexpr int TILE_MAX_PUNIQ = 256;      // unique neighbour pressure DoFs per tile
 
-struct TileSmem {
-  int4 desc[TILE_MAX_NODES * 2];
-  int idx[TILE_MAX_IDX];
-  int next, base_n, cnt_n, base_p;
+struct SpmvTiles {
+  const int* node_ptr;                   // [n_tiles+1] node ranges
+  const int* uniq_ptr;                   // [n_tiles+1] into uniq_xoff
+  const int* uniq_xoff;                  // x offset of (unique neighbour node, 0)
+  const int* puniq_ptr;                  // [n_tiles+1] into puniq_xoff
+  const int* puniq_xoff;                 // x offset of unique neighbour pressure DoFs
+  const unsigned short* nbr_loc;         // parallel to nbr_xoff: position in the tile's unique list
+  const unsigned short* pnbr_loc;        // parallel to pnbr_xoff
 };
 
-template <bool WITH_P>
-__device__ __forceinline__ void stage_tile(const DevMesh& M, int n0, int n1, TileSmem& T) {
+template <int DIM> struct TileSmem {
+  int4 desc[TILE_MAX_NODES * 2];
+  double xs[TILE_MAX_UNIQ * DIM + TILE_MAX_PUNIQ];
+  unsigned short idx[TILE_MAX_IDX];
+  int next, base_n, cnt_n, base_p, nuq;
+};
+
+template <int DIM, bool WITH_P>
+__device__ __forceinline__ void stage_tile(const DevMesh& M, const SpmvTiles& TL, int t, const double* __restrict__ x,
+                                           TileSmem<DIM>& T, int& n0, int& n1) {
+  n0 = TL.node_ptr[t]; n1 = TL.node_ptr[t + 1];
   const int nn = n1 - n0;
   const int4* g = reinterpret_cast<const int4*>(M.nd + n0);
   for (int i = threadIdx.x; i < 2 * nn; i += blockDim.x) T.desc[i] = __ldg(g + i);
+  // x values of the unique neighbours (independent of the descriptors)
+  const int u0 = TL.uniq_ptr[t], nuq = TL.uniq_ptr[t + 1] - u0;
+  for (int i = threadIdx.x; i < nuq * DIM; i += blockDim.x) T.xs[i] = __ldg(x + __ldg(TL.uniq_xoff + u0 + i / DIM) + i % DIM);
+  if (WITH_P) {
+    const int p0 = TL.puniq_ptr[t], npu = TL.puniq_ptr[t + 1] - p0;
+    for (int i = threadIdx.x; i < npu; i += blockDim.x) T.xs[nuq * DIM + i] = __ldg(x + __ldg(TL.puniq_xoff + p0 + i));
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     const int4 f = T.desc[1], l = T.desc[2 * nn - 1];
     T.base_n = f.x;
     T.cnt_n = l.x + (l.z & 0xffff) - f.x;
     T.base_p = f.y;
+    T.nuq = nuq;
     T.next = 0;
   }
   __syncthreads();
   const int base_n = T.base_n, cnt_n = T.cnt_n;
-  for (int i = threadIdx.x; i < cnt_n; i += blockDim.x) T.idx[i] = __ldg(M.nbr_xoff + base_n + i);
+  for (int i = threadIdx.x; i < cnt_n; i += blockDim.x) T.idx[i] = __ldg(TL.nbr_loc + base_n + i);
   if (WITH_P) {
     const int4 l = T.desc[2 * nn - 1];
     const int cnt_p = l.y + (int)((unsigned)l.z >> 16) - T.base_p;
-    for (int i = threadIdx.x; i < cnt_p; i += blockDim.x) T.idx[cnt_n + i] = __ldg(M.pnbr_xoff + T.base_p + i);
+    for (int i = threadIdx.x; i < cnt_p; i += blockDim.x) T.idx[cnt_n + i] = __ldg(TL.pnbr_loc + T.base_p + i);
   }
   __syncthreads();
 }
 
-__device__ __forceinline__ NodeDesc desc_from_smem(const TileSmem& T, int slot) {
+template <int DIM>
+__device__ __forceinline__ NodeDesc desc_from_smem(const TileSmem<DIM>& T, int slot) {
   const int4 a = T.desc[2 * slot], b = T.desc[2 * slot + 1];
   NodeDesc d;
   d.rowbase = ((long long)(unsigned)a.y << 32) | (unsigned)a.x;
@@ -111,61 +139,86 @@ __device__ __forceinline__ NodeDesc desc_from_smem(const TileSmem& T, int slot) 
   return d;
 }
 
+// sum[r] += sum_k row_r[k] * xs[pos(k)] with x staged in shared memory.
+// Columns k < nbd are velocity columns (DIM per neighbour node), the rest pressure columns.
+template <int DIM, int ROWS, typename VT>
+__device__ __forceinline__ void tile_row_dot(const VT* const (&rowp)[ROWS], int ncols, int nbd, const unsigned short* nx,
+                                             const unsigned short* px, const double* xs, int pbase, int lane,
+                                             double (&sum)[ROWS]) {
+  for (int k0 = 0; k0 < ncols; k0 += 32 * SPMV_UNROLL) {
+    VT v[ROWS][SPMV_UNROLL];
+    double xv[SPMV_UNROLL];
+#pragma unroll
+    for (int u = 0; u < SPMV_UNROLL; ++u) {
+      const int k = k0 + 32 * u + lane;
+      const bool ok = k < ncols;
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) v[r][u] = ok ? __ldcs(rowp[r] + k) : VT(0);
+      xv[u] = 0.0;
+      if (ok) xv[u] = (k < nbd) ? xs[(int)nx[k / DIM] * DIM + k % DIM] : xs[pbase + px[k - nbd]];
+    }
+#pragma unroll
+    for (int u = 0; u < SPMV_UNROLL; ++u)
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) sum[r] += (double)v[r][u] * xv[u];
+  }
+}
+
 // y = A x
 template <int DIM, typename VT>
 __global__ void __launch_bounds__(SPMV_WARPS * 32)
-k_spmv_full(DevMesh M, const int* __restrict__ tile_ptr, const VT* __restrict__ vals, const double* __restrict__ x,
-            double* __restrict__ y) {
-  __shared__ TileSmem T;
+k_spmv_full(DevMesh M, SpmvTiles TL, const VT* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y) {
+  __shared__ TileSmem<DIM> T;
   const int lane = threadIdx.x & 31;
-  const int n0 = tile_ptr[blockIdx.x], n1 = tile_ptr[blockIdx.x + 1];
-  stage_tile<true>(M, n0, n1, T);
+  int n0, n1;
+  stage_tile<DIM, true>(M, TL, blockIdx.x, x, T, n0, n1);
+  const int pbase = T.nuq * DIM;
   for (;;) {
-  int slot = 0;
-  if (lane == 0) slot = atomicAdd(&T.next, 1);
-  slot = __shfl_sync(NSB_FULL, slot, 0);
-  const int A = n0 + slot;
-  if (A >= n1) break;
-  const NodeDesc d = desc_from_smem(T, slot);
-  const int nbd = DIM * d.nb, len = nbd + d.np;
-  const int* nx = T.idx + (d.nbr0 - T.base_n);
-  const int* px = T.idx + T.cnt_n + (d.pnbr0 - T.base_p);
-  if (d.pid >= 0) {
-    const VT* rowp[DIM + 1];
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(&T.next, 1);
+    slot = __shfl_sync(NSB_FULL, slot, 0);
+    const int A = n0 + slot;
+    if (A >= n1) break;
+    const NodeDesc d = desc_from_smem(T, slot);
+    const int nbd = DIM * d.nb, len = nbd + d.np;
+    const unsigned short* nx = T.idx + (d.nbr0 - T.base_n);
+    const unsigned short* px = T.idx + T.cnt_n + (d.pnbr0 - T.base_p);
+    if (d.pid >= 0) {
+      const VT* rowp[DIM + 1];
 #pragma unroll
-    for (int c = 0; c < DIM; ++c) rowp[c] = vals + d.rowbase + (long long)c * len;
-    rowp[DIM] = vals + d.prowbase;
-    double sum[DIM + 1];
+      for (int c = 0; c < DIM; ++c) rowp[c] = vals + d.rowbase + (long long)c * len;
+      rowp[DIM] = vals + d.prowbase;
+      double sum[DIM + 1];
 #pragma unroll
-    for (int c = 0; c <= DIM; ++c) sum[c] = 0.0;
-    row_block_dot<DIM, DIM + 1, VT>(rowp, len, nbd, nx, px, x, lane, sum);
+      for (int c = 0; c <= DIM; ++c) sum[c] = 0.0;
+      tile_row_dot<DIM, DIM + 1, VT>(rowp, len, nbd, nx, px, T.xs, pbase, lane, sum);
 #pragma unroll
-    for (int c = 0; c <= DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
-    if (lane <= DIM) {
-      double v = sum[0];
+      for (int c = 0; c <= DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
+      if (lane <= DIM) {
+        double v = sum[0];
 #pragma unroll
-      for (int c = 1; c <= DIM; ++c) if (lane == c) v = sum[c];
-      if (lane < DIM) y[DIM * A + lane] = v;
-      else y[DIM * M.nn_own + d.pid] = v;
-    }
-  } else {
-    const VT* rowp[DIM];
+        for (int c = 1; c <= DIM; ++c) if (lane == c) v = sum[c];
+        if (lane < DIM) y[DIM * A + lane] = v;
+        else y[DIM * M.nn_own + d.pid] = v;
+      }
+    } else {
+      const VT* rowp[DIM];
 #pragma unroll
-    for (int c = 0; c < DIM; ++c) rowp[c] = vals + d.rowbase + (long long)c * len;
-    double sum[DIM];
+      for (int c = 0; c < DIM; ++c) rowp[c] = vals + d.rowbase + (long long)c * len;
+      double sum[DIM];
 #pragma unroll
-    for (int c = 0; c < DIM; ++c) sum[c] = 0.0;
-    row_block_dot<DIM, DIM, VT>(rowp, len, nbd, nx, px, x, lane, sum);
+      for (int c = 0; c < DIM; ++c) sum[c] = 0.0;
+      tile_row_dot<DIM, DIM, VT>(rowp, len, nbd, nx, px, T.xs, pbase, lane, sum);
 #pragma unroll
-    for (int c = 0; c < DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
-    if (lane < DIM) {
-      double v = sum[0];
+      for (int c = 0; c < DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
+      if (lane < DIM) {
+        double v = sum[0];
 #pragma unroll
-      for (int c = 1; c < DIM; ++c) if (lane == c) v = sum[c];
-      y[DIM * A + lane] = v;
+        for (int c = 1; c < DIM; ++c) if (lane == c) v = sum[c];
+        y[DIM * A + lane] = v;
+      }
     }
   }
-  }   // node loop
 }
 
 // ------------------------------------------------------------------------------------
@@ -181,32 +234,10 @@ struct PolyCoef {
   double cu, ct, cpu, cpy;
 };
 
-template <int DIM, int MODE, typename VT>
-__global__ void __launch_bounds__(SPMV_WARPS * 32)
-k_spmv_vel(DevMesh M, const int* __restrict__ tile_ptr, const VT* __restrict__ vals, const double* __restrict__ x,
-           double* __restrict__ y, const double* __restrict__ u, double* __restrict__ poly,
-           const double* __restrict__ dinv, PolyCoef pc) {
-  __shared__ TileSmem T;
-  const int lane = threadIdx.x & 31;
-  const int n0 = tile_ptr[blockIdx.x], n1 = tile_ptr[blockIdx.x + 1];
-  stage_tile<false>(M, n0, n1, T);
-  for (;;) {
-  int slot = 0;
-  if (lane == 0) slot = atomicAdd(&T.next, 1);
-  slot = __shfl_sync(NSB_FULL, slot, 0);
-  const int A = n0 + slot;
-  if (A >= n1) break;
-  const NodeDesc d = desc_from_smem(T, slot);
-  const int nbd = DIM * d.nb, len = nbd + d.np;
-  const VT* rowp[DIM];
-#pragma unroll
-  for (int c = 0; c < DIM; ++c) rowp[c] = vals + d.rowbase + (long long)c * len;
-  double sum[DIM];
-#pragma unroll
-  for (int c = 0; c < DIM; ++c) sum[c] = 0.0;
-  row_block_dot<DIM, DIM, VT>(rowp, nbd, nbd, T.idx + (d.nbr0 - T.base_n), nullptr, x, lane, sum);
-#pragma unroll
-  for (int c = 0; c < DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
+template <int DIM, int MODE>
+__device__ __forceinline__ void vel_epilogue(int A, int lane, const double (&sum)[DIM], double* __restrict__ y,
+                                             const double* __restrict__ u, double* __restrict__ poly,
+                                             const double* __restrict__ dinv, const PolyCoef& pc) {
   if (lane < DIM) {
     const int row = DIM * A + lane;
     if (MODE == 0) {
@@ -228,7 +259,35 @@ k_spmv_vel(DevMesh M, const int* __restrict__ tile_ptr, const VT* __restrict__ v
       }
     }
   }
-  }   // node loop
+}
+
+template <int DIM, int MODE, typename VT>
+__global__ void __launch_bounds__(SPMV_WARPS * 32)
+k_spmv_vel(DevMesh M, SpmvTiles TL, const VT* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+           const double* __restrict__ u, double* __restrict__ poly, const double* __restrict__ dinv, PolyCoef pc) {
+  __shared__ TileSmem<DIM> T;
+  const int lane = threadIdx.x & 31;
+  int n0, n1;
+  stage_tile<DIM, false>(M, TL, blockIdx.x, x, T, n0, n1);
+  for (;;) {
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(&T.next, 1);
+    slot = __shfl_sync(NSB_FULL, slot, 0);
+    const int A = n0 + slot;
+    if (A >= n1) break;
+    const NodeDesc d = desc_from_smem(T, slot);
+    const int nbd = DIM * d.nb, len = nbd + d.np;
+    const VT* rowp[DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) rowp[c] = vals + d.rowbase + (long long)c * len;
+    double sum[DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) sum[c] = 0.0;
+    tile_row_dot<DIM, DIM, VT>(rowp, nbd, nbd, T.idx + (d.nbr0 - T.base_n), nullptr, T.xs, 0, lane, sum);
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
+    vel_epilogue<DIM, MODE>(A, lane, sum, y, u, poly, dinv, pc);
+  }
 }
 
 // Same operator and epilogues as k_spmv_vel, reading the PRIVATE fp32 copy of F that the assembly
@@ -241,14 +300,14 @@ template <> struct F32Vec<2> { using type = float2; };
 
 template <int DIM, int MODE>
 __global__ void __launch_bounds__(SPMV_WARPS * 32)
-k_spmv_vel_f32(DevMesh M, const int* __restrict__ tile_ptr, const typename F32Vec<DIM>::type* __restrict__ fv,
+k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __restrict__ fv,
                const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ u,
                double* __restrict__ poly, const double* __restrict__ dinv, PolyCoef pc) {
   using V = typename F32Vec<DIM>::type;
-  __shared__ TileSmem T;
+  __shared__ TileSmem<DIM> T;
   const int lane = threadIdx.x & 31;
-  const int n0 = tile_ptr[blockIdx.x], n1 = tile_ptr[blockIdx.x + 1];
-  stage_tile<false>(M, n0, n1, T);
+  int n0, n1;
+  stage_tile<DIM, false>(M, TL, blockIdx.x, x, T, n0, n1);
   for (;;) {
     int slot = 0;
     if (lane == 0) slot = atomicAdd(&T.next, 1);
@@ -258,24 +317,20 @@ k_spmv_vel_f32(DevMesh M, const int* __restrict__ tile_ptr, const typename F32Ve
     const NodeDesc d = desc_from_smem(T, slot);
     const int nbd = DIM * d.nb;
     const V* rp = fv + (long long)DIM * d.nbr0;
-    const int* nx = T.idx + (d.nbr0 - T.base_n);
+    const unsigned short* nx = T.idx + (d.nbr0 - T.base_n);
     double sum[DIM];
 #pragma unroll
     for (int c = 0; c < DIM; ++c) sum[c] = 0.0;
     for (int k0 = 0; k0 < nbd; k0 += 32 * SPMV_UNROLL) {
       V v[SPMV_UNROLL];
-      int xo[SPMV_UNROLL];
       double xv[SPMV_UNROLL];
 #pragma unroll
       for (int q = 0; q < SPMV_UNROLL; ++q) {
         const int k = k0 + 32 * q + lane;
-        const bool ok = k < nbd;
         v[q] = V();
-        xo[q] = -1;
-        if (ok) { v[q] = __ldcs(rp + k); xo[q] = nx[k / DIM] + k % DIM; }
+        xv[q] = 0.0;
+        if (k < nbd) { v[q] = __ldcs(rp + k); xv[q] = T.xs[(int)nx[k / DIM] * DIM + k % DIM]; }
       }
-#pragma unroll
-      for (int q = 0; q < SPMV_UNROLL; ++q) xv[q] = xo[q] >= 0 ? __ldg(x + xo[q]) : 0.0;
 #pragma unroll
       for (int q = 0; q < SPMV_UNROLL; ++q) {
         sum[0] += (double)v[q].x * xv[q];
@@ -285,20 +340,7 @@ k_spmv_vel_f32(DevMesh M, const int* __restrict__ tile_ptr, const typename F32Ve
     }
 #pragma unroll
     for (int c = 0; c < DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
-    if (lane < DIM) {
-      const int row = DIM * A + lane;
-      double t = 0.0;
-#pragma unroll
-      for (int c = 0; c < DIM; ++c) t += dinv[(size_t)A * DIM * DIM + lane * DIM + c] * sum[c];
-      if (MODE == 2) {
-        y[row] = t;
-      } else {
-        const double uv = u[row];
-        const double yv = pc.cu * uv + pc.ct * t;
-        y[row] = yv;
-        poly[row] += pc.cpu * uv + pc.cpy * yv;
-      }
-    }
+    vel_epilogue<DIM, MODE>(A, lane, sum, y, u, poly, dinv, pc);
   }
 }
 

@@ -190,7 +190,9 @@ struct nsb_ctx {
   DBuf<FeTables> d_fe;              // L2-resident copy of the FE tables (kernels stage it in shared memory)
   int num_sms = 148;
   int n_tiles = 0, tile_smem_bytes = 0;
-  DBuf<int> d_stile_ptr;            // SpMV tiles (descriptor + index staging in shared memory)
+  DBuf<int> d_stile_ptr, d_suniq_ptr, d_suniq_xoff, d_spuniq_ptr, d_spuniq_xoff;   // SpMV tiles (see linalg.cuh)
+  DBuf<unsigned short> d_nbr_loc, d_pnbr_loc;
+  SpmvTiles stiles{};
   int n_stiles = 0;
   // global dof -> local vector offset (or -1)
   std::vector<int> g2x;
@@ -339,8 +341,8 @@ template <int DIM> void set_smem_attr(int bytes) {
 // y(owned) = A x ; x must have a valid ghost tail
 void spmv_full(nsb_ctx* c, const double* x, double* y) {
   size_t id = c->prof.begin(PC_SPMV, c->stream);
-  if (c->dim == 2) k_spmv_full<2, double><<<c->n_stiles, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, c->vals.p, x, y);
-  else k_spmv_full<3, double><<<c->n_stiles, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, c->vals.p, x, y);
+  if (c->dim == 2) k_spmv_full<2, double><<<c->n_stiles, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, c->vals.p, x, y);
+  else k_spmv_full<3, double><<<c->n_stiles, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, c->vals.p, x, y);
   c->launch_check();
   c->prof.end(id, c->stream);
 }
@@ -350,11 +352,11 @@ void spmv_vel(nsb_ctx* c, const double* x, double* y, const double* u, double* p
   size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
   const int g = c->n_stiles;
   if (c->vals_f.p && MODE != 0) {
-    if (c->dim == 2) k_spmv_vel_f32<2, MODE><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, reinterpret_cast<const float2*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
-    else k_spmv_vel_f32<3, MODE><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, reinterpret_cast<const float4*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
+    if (c->dim == 2) k_spmv_vel_f32<2, MODE><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float2*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
+    else k_spmv_vel_f32<3, MODE><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float4*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
   } else {
-    if (c->dim == 2) k_spmv_vel<2, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, c->vals.p, x, y, u, poly, c->dinv.p, pc);
-    else k_spmv_vel<3, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->d_stile_ptr.p, c->vals.p, x, y, u, poly, c->dinv.p, pc);
+    if (c->dim == 2) k_spmv_vel<2, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, c->vals.p, x, y, u, poly, c->dinv.p, pc);
+    else k_spmv_vel<3, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, c->vals.p, x, y, u, poly, c->dinv.p, pc);
   }
   c->launch_check();
   c->prof.end(id, c->stream);
@@ -806,19 +808,57 @@ void build_tiles(nsb_ctx* c) {
   c->n_tiles = (int)tp.size() - 1;
   c->tile_smem_bytes = budget * 8;
   c->d_tile_ptr.upload(tp, c->stream);
-  // SpMV tiles: at most TILE_MAX_NODES nodes and TILE_MAX_IDX staged neighbour offsets
-  std::vector<int> sp;
-  sp.push_back(0);
-  int idx = 0, cn = 0;
-  for (int A = 0; A < S.nn_own; ++A) {
-    const int need = (int)(S.nbr_ptr[A + 1] - S.nbr_ptr[A]) + (int)(S.pnbr_ptr[A + 1] - S.pnbr_ptr[A]);
-    if (need > TILE_MAX_IDX) throw CudaErr{"a node has more neighbours than one SpMV tile can stage"};
-    if (cn > 0 && (idx + need > TILE_MAX_IDX || cn >= TILE_MAX_NODES)) { sp.push_back(A); idx = 0; cn = 0; }
-    idx += need; ++cn;
+  // SpMV tiles: consecutive nodes with bounded staged index count and bounded UNIQUE neighbour sets
+  {
+    const int ntot = S.nn_own + S.nn_ghost, ptot = S.np_own + S.np_ghost;
+    std::vector<int> sp, uptr, uxoff, pptr, pxoff;
+    std::vector<unsigned short> nloc(S.nbr.size()), ploc(S.pnbr.size());
+    std::vector<int> stamp(ntot, -1), pstamp(ptot, -1), posn(ntot, 0), posp(ptot, 0);
+    sp.push_back(0); uptr.push_back(0); pptr.push_back(0);
+    int A = 0, tile = 0;
+    std::vector<int> U, PU;
+    while (A < S.nn_own) {
+      U.clear(); PU.clear();
+      int idx = 0, cn = 0;
+      const int start = A;
+      while (A < S.nn_own && cn < TILE_MAX_NODES) {
+        const int nb = (int)(S.nbr_ptr[A + 1] - S.nbr_ptr[A]), np = (int)(S.pnbr_ptr[A + 1] - S.pnbr_ptr[A]);
+        if (nb + np > TILE_MAX_IDX || nb > TILE_MAX_UNIQ || np > TILE_MAX_PUNIQ)
+          throw CudaErr{"a node has more neighbours than one SpMV tile can stage"};
+        if (idx + nb + np > TILE_MAX_IDX) break;
+        int newu = 0, newp = 0;
+        for (int64_t k = S.nbr_ptr[A]; k < S.nbr_ptr[A + 1]; ++k) newu += stamp[S.nbr[k]] != tile;
+        for (int64_t k = S.pnbr_ptr[A]; k < S.pnbr_ptr[A + 1]; ++k) newp += pstamp[S.pnbr[k]] != tile;
+        if ((int)U.size() + newu > TILE_MAX_UNIQ || (int)PU.size() + newp > TILE_MAX_PUNIQ) break;
+        for (int64_t k = S.nbr_ptr[A]; k < S.nbr_ptr[A + 1]; ++k)
+          if (stamp[S.nbr[k]] != tile) { stamp[S.nbr[k]] = tile; U.push_back(S.nbr[k]); }
+        for (int64_t k = S.pnbr_ptr[A]; k < S.pnbr_ptr[A + 1]; ++k)
+          if (pstamp[S.pnbr[k]] != tile) { pstamp[S.pnbr[k]] = tile; PU.push_back(S.pnbr[k]); }
+        idx += nb + np; ++cn; ++A;
+      }
+      // memory order, then positions
+      std::sort(U.begin(), U.end(), [&](int a, int b) { return S.node_xoff(a) < S.node_xoff(b); });
+      std::sort(PU.begin(), PU.end(), [&](int a, int b) { return S.pid_xoff(a) < S.pid_xoff(b); });
+      for (size_t i = 0; i < U.size(); ++i) { posn[U[i]] = (int)i; uxoff.push_back((int)S.node_xoff(U[i])); }
+      for (size_t i = 0; i < PU.size(); ++i) { posp[PU[i]] = (int)i; pxoff.push_back((int)S.pid_xoff(PU[i])); }
+      for (int B = start; B < A; ++B) {
+        for (int64_t k = S.nbr_ptr[B]; k < S.nbr_ptr[B + 1]; ++k) nloc[k] = (unsigned short)posn[S.nbr[k]];
+        for (int64_t k = S.pnbr_ptr[B]; k < S.pnbr_ptr[B + 1]; ++k) ploc[k] = (unsigned short)posp[S.pnbr[k]];
+      }
+      sp.push_back(A); uptr.push_back((int)uxoff.size()); pptr.push_back((int)pxoff.size());
+      ++tile;
+    }
+    c->n_stiles = (int)sp.size() - 1;
+    c->d_stile_ptr.upload(sp, c->stream);
+    c->d_suniq_ptr.upload(uptr, c->stream); c->d_suniq_xoff.upload(uxoff, c->stream);
+    c->d_spuniq_ptr.upload(pptr, c->stream); c->d_spuniq_xoff.upload(pxoff, c->stream);
+    c->d_nbr_loc.upload(nloc, c->stream); c->d_pnbr_loc.upload(ploc, c->stream);
+    CK(cudaStreamSynchronize(c->stream));
+    c->stiles.node_ptr = c->d_stile_ptr.p;
+    c->stiles.uniq_ptr = c->d_suniq_ptr.p; c->stiles.uniq_xoff = c->d_suniq_xoff.p;
+    c->stiles.puniq_ptr = c->d_spuniq_ptr.p; c->stiles.puniq_xoff = c->d_spuniq_xoff.p;
+    c->stiles.nbr_loc = c->d_nbr_loc.p; c->stiles.pnbr_loc = c->d_pnbr_loc.p;
   }
-  sp.push_back(S.nn_own);
-  c->n_stiles = (int)sp.size() - 1;
-  c->d_stile_ptr.upload(sp, c->stream);
   CK(cudaStreamSynchronize(c->stream));
   if (c->dim == 2) set_smem_attr<2>(c->tile_smem_bytes);
   else set_smem_attr<3>(c->tile_smem_bytes);
