@@ -251,6 +251,7 @@ def main():
     ms = dev.timer_stop()
     sync_all()
     launches = dev.launch_count() - launches0
+    log("[bench] rank %d timed region done: %.1f ms for %d steps" % (rank, ms, args.steps))
     prof = dev.profile()
     dev.profile_enable(False)
     t_res = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -265,6 +266,7 @@ def main():
         step_e2e()
     ms_e2e = dev.timer_stop()
     sync_all()
+    log("[bench] rank %d e2e region done: %.1f ms" % (rank, ms_e2e))
     t_e = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)

@@ -40,6 +40,8 @@ typedef struct nsb_params {
 typedef struct nsb_solver_opts {
   int32_t poly_degree_F;    /* max degree of the GMRES polynomial on Dinv*F  (default 32)  */
   int32_t poly_refresh;     /* rebuild that polynomial every k-th solve      (default 1)   */
+  int32_t poly_kind;        /* 0 = GMRES polynomial (harmonic Ritz roots, default); 1 = Chebyshev roots on the
+                               interval spanned by the Ritz values when the spectrum is real      */
   double poly_target;       /* stop growing the degree once the polynomial reduces the probe
                                vector's residual below this                  (default 0.12) */
   int32_t cheb_degree_Mp;   /* Jacobi Chebyshev degree on M_p               (default 3)   */

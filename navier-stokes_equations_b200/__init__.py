@@ -30,7 +30,7 @@ class NsbParams(C.Structure):
 
 
 class NsbSolverOpts(C.Structure):
-    _fields_ = [("poly_degree_F", C.c_int32), ("poly_refresh", C.c_int32), ("poly_target", C.c_double), ("cheb_degree_Mp", C.c_int32),
+    _fields_ = [("poly_degree_F", C.c_int32), ("poly_refresh", C.c_int32), ("poly_kind", C.c_int32), ("poly_target", C.c_double), ("cheb_degree_Mp", C.c_int32),
                 ("amg_smoother_degree", C.c_int32), ("schur_mass_coeff", C.c_double), ("reorthogonalize", C.c_int32), ("precond_precision", C.c_int32)]
 
 
@@ -140,9 +140,9 @@ class Device:
         p = NsbParams(dt, theta, nu, rho, gamma, int(use_supg), int(first_order_ustar))
         self._ck(lib().nsb_set_params(self.h, C.byref(p)))
 
-    def set_solver_opts(self, poly_degree_F=0, poly_refresh=0, poly_target=0.0, cheb_degree_Mp=0, amg_smoother_degree=0,
+    def set_solver_opts(self, poly_degree_F=0, poly_refresh=0, poly_kind=0, poly_target=0.0, cheb_degree_Mp=0, amg_smoother_degree=0,
                         schur_mass_coeff=0.0, reorthogonalize=1, precond_precision=0):
-        o = NsbSolverOpts(poly_degree_F, poly_refresh, poly_target, cheb_degree_Mp, amg_smoother_degree, schur_mass_coeff, reorthogonalize, precond_precision)
+        o = NsbSolverOpts(poly_degree_F, poly_refresh, poly_kind, poly_target, cheb_degree_Mp, amg_smoother_degree, schur_mass_coeff, reorthogonalize, precond_precision)
         self._ck(lib().nsb_set_solver_opts(self.h, C.byref(o)))
 
     def set_vector(self, which, v):

@@ -298,8 +298,6 @@ k_spmv_vel(DevMesh M, SpmvTiles TL, const VT* __restrict__ vals, const double* _
 template <int DIM> struct F32Vec { using type = float4; };
 template <> struct F32Vec<2> { using type = float2; };
 
-constexpr int F32_PRE = 3;                 // prefetched chunks of 32 columns (covers the 81 columns of a line node)
-
 template <int DIM, int MODE>
 __global__ void __launch_bounds__(SPMV_WARPS * 32)
 k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __restrict__ fv,
@@ -307,74 +305,42 @@ k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __rest
                double* __restrict__ poly, const double* __restrict__ dinv, PolyCoef pc) {
   using V = typename F32Vec<DIM>::type;
   __shared__ TileSmem<DIM> T;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   int n0, n1;
   stage_tile<DIM, false>(M, TL, blockIdx.x, x, T, n0, n1);
-  const int nn = n1 - n0;
-  // Software pipeline over this warp's nodes (static assignment wid, wid+8, ...): the value loads of the
-  // NEXT node are in flight while the current node is multiplied, reduced and written, so the per-node
-  // latency chain (loads -> FMAs -> shuffle reduction -> epilogue) no longer serialises.
-  V vcur[F32_PRE], vnxt[F32_PRE];
-  auto issue = [&](int slot, V (&v)[F32_PRE]) {
-    const int4 b4 = T.desc[2 * slot + 1];
-    const int nbd = DIM * (b4.z & 0xffff);
-    const V* rp = fv + (long long)DIM * b4.x;
-#pragma unroll
-    for (int q = 0; q < F32_PRE; ++q) {
-      const int k = 32 * q + lane;
-      v[q] = V();
-      if (k < nbd) v[q] = __ldcs(rp + k);
-    }
-  };
-  int slot = wid;
-  if (slot < nn) issue(slot, vcur);
-  while (slot < nn) {
-    const int nslot = slot + SPMV_WARPS;
-    if (nslot < nn) issue(nslot, vnxt);
-    const int4 b4 = T.desc[2 * slot + 1];
-    const int nbr0 = b4.x, nbd = DIM * (b4.z & 0xffff);
-    const unsigned short* nx = T.idx + (nbr0 - T.base_n);
+  for (;;) {
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(&T.next, 1);
+    slot = __shfl_sync(NSB_FULL, slot, 0);
+    const int A = n0 + slot;
+    if (A >= n1) break;
+    const NodeDesc d = desc_from_smem(T, slot);
+    const int nbd = DIM * d.nb;
+    const V* rp = fv + (long long)DIM * d.nbr0;
+    const unsigned short* nx = T.idx + (d.nbr0 - T.base_n);
     double sum[DIM];
 #pragma unroll
     for (int c = 0; c < DIM; ++c) sum[c] = 0.0;
+    for (int k0 = 0; k0 < nbd; k0 += 32 * SPMV_UNROLL) {
+      V v[SPMV_UNROLL];
+      double xv[SPMV_UNROLL];
 #pragma unroll
-    for (int q = 0; q < F32_PRE; ++q) {
-      const int k = 32 * q + lane;
-      if (k < nbd) {
-        const double xv = T.xs[(int)nx[k / DIM] * DIM + k % DIM];
-        sum[0] += (double)vcur[q].x * xv;
-        sum[1] += (double)vcur[q].y * xv;
-        if (DIM == 3) sum[DIM - 1] += (double)reinterpret_cast<const float*>(&vcur[q])[DIM - 1] * xv;
+      for (int q = 0; q < SPMV_UNROLL; ++q) {
+        const int k = k0 + 32 * q + lane;
+        v[q] = V();
+        xv[q] = 0.0;
+        if (k < nbd) { v[q] = __ldcs(rp + k); xv[q] = T.xs[(int)nx[k / DIM] * DIM + k % DIM]; }
       }
-    }
-    if (nbd > 32 * F32_PRE) {                     // vertex nodes: remaining columns, not prefetched
-      const V* rp = fv + (long long)DIM * nbr0;
-      for (int k0 = 32 * F32_PRE; k0 < nbd; k0 += 32 * SPMV_UNROLL) {
-        V v[SPMV_UNROLL];
 #pragma unroll
-        for (int q = 0; q < SPMV_UNROLL; ++q) {
-          const int k = k0 + 32 * q + lane;
-          v[q] = V();
-          if (k < nbd) v[q] = __ldcs(rp + k);
-        }
-#pragma unroll
-        for (int q = 0; q < SPMV_UNROLL; ++q) {
-          const int k = k0 + 32 * q + lane;
-          if (k < nbd) {
-            const double xv = T.xs[(int)nx[k / DIM] * DIM + k % DIM];
-            sum[0] += (double)v[q].x * xv;
-            sum[1] += (double)v[q].y * xv;
-            if (DIM == 3) sum[DIM - 1] += (double)reinterpret_cast<const float*>(&v[q])[DIM - 1] * xv;
-          }
-        }
+      for (int q = 0; q < SPMV_UNROLL; ++q) {
+        sum[0] += (double)v[q].x * xv[q];
+        sum[1] += (double)v[q].y * xv[q];
+        if (DIM == 3) sum[DIM - 1] += (double)reinterpret_cast<const float*>(&v[q])[DIM - 1] * xv[q];
       }
     }
 #pragma unroll
     for (int c = 0; c < DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
-    vel_epilogue<DIM, MODE>(n0 + slot, lane, sum, y, u, poly, dinv, pc);
-#pragma unroll
-    for (int q = 0; q < F32_PRE; ++q) vcur[q] = vnxt[q];
-    slot = nslot;
+    vel_epilogue<DIM, MODE>(A, lane, sum, y, u, poly, dinv, pc);
   }
 }
 

@@ -415,12 +415,17 @@ void setup_F_poly(nsb_ctx* c) {
   if (c->partial.n < (size_t)nb * (d + 2)) c->partial.alloc((size_t)nb * (d + 2));
   if (c->d_h.n < (size_t)2 * (d + 2)) c->d_h.alloc(2 * (d + 2));
   if (!c->eig_init) {
+    // pseudo-random probe, a function of the GLOBAL DoF index only -> the polynomial (and therefore the
+    // GMRES iteration count) does not depend on how the mesh is partitioned
     std::vector<double> h(nu);
-    uint64_t s = 0x2545F4914F6CDD1Dull;
-    for (long long i = 0; i < nu; ++i) {
-      s ^= s << 13; s ^= s >> 7; s ^= s << 17;
-      h[i] = (double)(s >> 11) / 9007199254740992.0 - 0.5;
-    }
+    for (int A = 0; A < S.nn_own; ++A)
+      for (int k = 0; k < c->dim; ++k) {
+        uint64_t z = (uint64_t)(S.node_gid[A] * c->dim + k) + 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        h[(size_t)c->dim * A + k] = (double)(z >> 11) / 9007199254740992.0 - 0.5;
+      }
     c->eigv.upload(h, c->stream);
     CK(cudaStreamSynchronize(c->stream));
     c->eig_init = true;
@@ -512,6 +517,16 @@ void setup_F_poly(nsb_ctx* c) {
   if (!hessenberg_eigs(d, Hd, wr, wi)) throw CudaErr{"harmonic Ritz eigenvalue iteration did not converge"};
   // Leja ordering, complex conjugates kept adjacent (positive imaginary part first)
   std::vector<std::pair<double, double>> th, out;
+  if (c->opt.poly_kind == 1) {
+    // Chebyshev roots on the real interval spanned by the Ritz values (minimax instead of probe-optimal);
+    // only meaningful when the spectrum is essentially real
+    double lo = 1e300, hi = -1e300, im = 0;
+    for (int i = 0; i < d; ++i) { lo = std::min(lo, wr[i]); hi = std::max(hi, wr[i]); im = std::max(im, std::fabs(wi[i])); }
+    if (lo > 0 && im < 0.05 * hi) {
+      lo *= 0.9; hi *= 1.05;
+      for (int j = 1; j <= d; ++j) { wr[j - 1] = 0.5 * (hi + lo) + 0.5 * (hi - lo) * std::cos(M_PI * (2 * j - 1) / (2.0 * d)); wi[j - 1] = 0; }
+    }
+  }
   for (int i = 0; i < d; ++i) if (wi[i] >= 0) th.emplace_back(wr[i], wi[i]);
   auto mag = [](const std::pair<double, double>& z) { return std::hypot(z.first, z.second); };
   while (!th.empty()) {

@@ -53,11 +53,8 @@ def main():
     print(f"pressure matrices + AMG {time.time()-t0:.1f}s", flush=True)
     asm_bytes = 8 * nnz + 8 * nrows + 8 * 3 * 4 * nc + 20 * 34 * nc
     spmv_bytes = 12 * nnz + 16 * nrows + 4 * (nrows + 1)
-    sweeps = [dict(poly_target=0.08, poly_degree_F=32)]
-    if len(sys.argv) > 3:
-        sweeps = [dict(poly_target=0.05, poly_degree_F=64), dict(poly_target=0.03, poly_degree_F=64),
-                  dict(poly_target=0.08, poly_degree_F=32, amg_smoother_degree=4),
-                  dict(poly_target=0.08, poly_degree_F=32, schur_mass_coeff=0.5e-3)]
+    sweeps = [dict(poly_target=0.05, poly_degree_F=64), dict(poly_target=0.05, poly_degree_F=64, poly_kind=1),
+              dict(poly_target=0.08, poly_degree_F=64, poly_kind=1), dict(poly_target=0.03, poly_degree_F=64, poly_kind=1)]
     for deg in sweeps:
         dev.set_solver_opts(**deg)
         dev.profile_enable(True)
