@@ -203,7 +203,6 @@ def main():
     un, unm1 = synthetic_state(sp_pts, comp, n_u)
     dev.set_constraints(cdofs, cvals)
     dev.set_params(0.01, 0.5, 1e-3, 1.0, 0.1, True, False)
-    dev.set_solver_opts(poly_degree_F=64, poly_target=0.05)
     dev.set_vector(nsb.NSB_SOLUTION_OLD, un)
     dev.set_vector(nsb.NSB_SOLUTION_OLD_OLD, unm1)
     dev.assemble_linearized()

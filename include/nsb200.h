@@ -38,12 +38,13 @@ typedef struct nsb_params {
 /* options of the GPU preconditioner that stands in for Ifpack ILU / ML AMG
  * (reference NavierStokes.hpp:302-315).  Zero-initialise for defaults. */
 typedef struct nsb_solver_opts {
-  int32_t poly_degree_F;    /* max degree of the GMRES polynomial on Dinv*F  (default 32)  */
+  int32_t poly_degree_F;    /* max degree of the polynomial on Dinv*F        (default 64)  */
   int32_t poly_refresh;     /* rebuild that polynomial every k-th solve      (default 1)   */
-  int32_t poly_kind;        /* 0 = GMRES polynomial (harmonic Ritz roots, default); 1 = Chebyshev roots on the
-                               interval spanned by the Ritz values when the spectrum is real      */
+  int32_t poly_kind;        /* 0/1 = Chebyshev roots on the interval spanned by the harmonic Ritz values when the
+                               spectrum is real, else the harmonic Ritz roots themselves (default);
+                               <0 = always the harmonic Ritz (GMRES) polynomial                       */
   double poly_target;       /* stop growing the degree once the polynomial reduces the probe
-                               vector's residual below this                  (default 0.12) */
+                               vector's residual below this                  (default 0.08) */
   int32_t cheb_degree_Mp;   /* Jacobi Chebyshev degree on M_p               (default 3)   */
   int32_t amg_smoother_degree; /* Chebyshev sweeps per level, pre and post  (default 2)   */
   double schur_mass_coeff;  /* coefficient of M_p^-1; <0 = theta*nu + gamma_graddiv (default),

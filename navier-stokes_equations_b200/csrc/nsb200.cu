@@ -1001,7 +1001,7 @@ int nsb_create(int dim, int device, nsb_handle* out) {
     CK(cudaStreamSynchronize(c->stream));
   }
   CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
-  c->opt.poly_degree_F = 32; c->opt.poly_refresh = 1; c->opt.poly_target = 0.12; c->opt.cheb_degree_Mp = 3;
+  c->opt.poly_degree_F = 64; c->opt.poly_refresh = 1; c->opt.poly_target = 0.08; c->opt.poly_kind = 1; c->opt.cheb_degree_Mp = 3;
   c->opt.amg_smoother_degree = 2; c->opt.schur_mass_coeff = -1.0; c->opt.reorthogonalize = 1; c->opt.precond_precision = 32;
   c->par.dt = 0.01; c->par.theta = 1.0; c->par.nu = 1e-3; c->par.rho = 1.0; c->par.gamma = 0.1;
   c->d_nrm.alloc(4);
@@ -1250,8 +1250,10 @@ int nsb_set_params(nsb_handle c, const nsb_params* p) {
 int nsb_set_solver_opts(nsb_handle c, const nsb_solver_opts* o) {
   if (!c || !o) return -1;
   nsb_solver_opts n = *o;
-  if (n.poly_degree_F <= 0) n.poly_degree_F = 32;
-  if (!(n.poly_target > 0)) n.poly_target = 0.12;
+  if (n.poly_degree_F <= 0) n.poly_degree_F = 64;
+  if (!(n.poly_target > 0)) n.poly_target = 0.08;
+  if (n.poly_kind == 0) n.poly_kind = 1;          // 0 = default (Chebyshev roots when the spectrum is real)
+  else if (n.poly_kind < 0) n.poly_kind = 0;      // negative = force the harmonic-Ritz (GMRES) polynomial
   if (n.poly_refresh <= 0) n.poly_refresh = 1;
   if (n.cheb_degree_Mp <= 0) n.cheb_degree_Mp = 3;
   if (n.amg_smoother_degree <= 0) n.amg_smoother_degree = 2;
