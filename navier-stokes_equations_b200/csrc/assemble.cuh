@@ -291,7 +291,7 @@ struct RowOut {
 };
 
 template <int DIM, bool NEWTON>
-__global__ void __launch_bounds__(ASM_WARPS * 32)
+__global__ void __launch_bounds__(ASM_WARPS * 32, NEWTON ? 2 : 3)
 k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double* __restrict__ cell_rhs,
             const unsigned char* __restrict__ cflag, const double* __restrict__ cval, RowOut out,
             const int* __restrict__ tile_ptr, const FeTables* __restrict__ gT) {
@@ -380,18 +380,47 @@ k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double
     double racc = 0.0;                                         // lane c < rows accumulates rhs row c
     __syncwarp();
 
-    for (long long kc = M.n2c_ptr[A]; kc < M.n2c_ptr[A + 1]; ++kc) {
-      const uint32_t pk = __ldg(M.n2c + kc);
-      const int cell = (int)(pk >> 4), a = (int)(pk & 15u);
-      // stage the cell context
-      const double* cg = ctx + (size_t)cell * CTXN;
-      for (int k = lane; k < CTXN; k += 32) sc[k] = __ldg(cg + k);
-      const int rb = __ldg(M.rank_uu + ((size_t)cell * NN + a) * NN + b);
-      int rp = 0;
-      if (lane < DIM * NV) rp = __ldg(M.rank_up + ((size_t)cell * NN + a) * NV + lane / DIM);
+    // The node's (cell, local index) list is read with one coalesced load per 32 cells; the global
+    // data of cell i+1 (context, neighbour ranks, rhs entry) is fetched into registers while cell i is
+    // being processed, so no global-memory latency sits on the dependent chain of the cell loop.
+    constexpr int NCW = (CTXN + 31) / 32;                  // context words per lane
+    const long long kc0 = M.n2c_ptr[A];
+    const int ncell = (int)(M.n2c_ptr[A + 1] - kc0);
+    uint32_t pk_lane = 0;
+    double nctx[NCW];
+    int nrb = 0, nrp = 0;
+    double nrh = 0.0;
+    auto fetch = [&](uint32_t pk) {
+      const int cell_ = (int)(pk >> 4), a_ = (int)(pk & 15u);
+      const double* cg = ctx + (size_t)cell_ * CTXN;
+#pragma unroll
+      for (int w = 0; w < NCW; ++w) nctx[w] = (lane + 32 * w < CTXN) ? __ldg(cg + lane + 32 * w) : 0.0;
+      nrb = __ldg(M.rank_uu + ((size_t)cell_ * NN + a_) * NN + b);
+      nrp = (lane < DIM * NV) ? (int)__ldg(M.rank_up + ((size_t)cell_ * NN + a_) * NV + lane / DIM) : 0;
+      nrh = 0.0;
       if (lane < rows) {
-        const int li = (lane < DIM) ? a * DIM + lane : NN * DIM + a;
-        racc += __ldg(cell_rhs + (size_t)cell * DPC + li);
+        const int li = (lane < DIM) ? a_ * DIM + lane : NN * DIM + a_;
+        nrh = __ldg(cell_rhs + (size_t)cell_ * DPC + li);
+      }
+    };
+    if (ncell > 0) {
+      pk_lane = (lane < ncell) ? __ldg(M.n2c + kc0 + lane) : 0u;
+      fetch(__shfl_sync(NSB_FULL, pk_lane, 0));
+    }
+    for (int ic = 0; ic < ncell; ++ic) {
+      if (ic > 0 && (ic & 31) == 0) pk_lane = (ic + lane < ncell) ? __ldg(M.n2c + kc0 + ic + lane) : 0u;
+      const uint32_t pk = __shfl_sync(NSB_FULL, pk_lane, ic & 31);
+      const int a = (int)(pk & 15u);
+      // publish the prefetched data of this cell, then start fetching the next one
+#pragma unroll
+      for (int w = 0; w < NCW; ++w) if (lane + 32 * w < CTXN) sc[lane + 32 * w] = nctx[w];
+      const int rb = nrb, rp = nrp;
+      racc += nrh;
+      if (ic + 1 < ncell) {
+        uint32_t pkn;
+        if (((ic + 1) & 31) == 0) pkn = __ldg(M.n2c + kc0 + ic + 1);
+        else pkn = __shfl_sync(NSB_FULL, pk_lane, (ic + 1) & 31);
+        fetch(pkn);
       }
       __syncwarp();
       const double absJ = sc[C::ABSJ];
