@@ -234,10 +234,28 @@ struct PolyCoef {
   double cu, ct, cpu, cpy;
 };
 
+// Operands of the fused epilogue, fetched at node start so that their latency overlaps the value stream.
+template <int DIM> struct EpiOps {
+  double dv[DIM];      // row `lane` of the inverse node-diagonal block
+  double uv, pv;       // u[row], poly[row]
+};
+
+template <int DIM, int MODE>
+__device__ __forceinline__ void vel_prefetch(int A, int lane, const double* __restrict__ u, const double* __restrict__ poly,
+                                             const double* __restrict__ dinv, EpiOps<DIM>& e) {
+  e.uv = 0.0; e.pv = 0.0;
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) e.dv[c] = 0.0;
+  if (MODE != 0 && lane < DIM) {
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) e.dv[c] = __ldg(dinv + (size_t)A * DIM * DIM + lane * DIM + c);
+    if (MODE == 3) { e.uv = u[DIM * A + lane]; e.pv = poly[DIM * A + lane]; }
+  }
+}
+
 template <int DIM, int MODE>
 __device__ __forceinline__ void vel_epilogue(int A, int lane, const double (&sum)[DIM], double* __restrict__ y,
-                                             const double* __restrict__ u, double* __restrict__ poly,
-                                             const double* __restrict__ dinv, const PolyCoef& pc) {
+                                             double* __restrict__ poly, const EpiOps<DIM>& e, const PolyCoef& pc) {
   if (lane < DIM) {
     const int row = DIM * A + lane;
     if (MODE == 0) {
@@ -248,14 +266,13 @@ __device__ __forceinline__ void vel_epilogue(int A, int lane, const double (&sum
     } else {
       double t = 0.0;
 #pragma unroll
-      for (int c = 0; c < DIM; ++c) t += dinv[(size_t)A * DIM * DIM + lane * DIM + c] * sum[c];
+      for (int c = 0; c < DIM; ++c) t += e.dv[c] * sum[c];
       if (MODE == 2) {
         y[row] = t;
       } else {
-        const double uv = u[row];
-        const double yv = pc.cu * uv + pc.ct * t;
+        const double yv = pc.cu * e.uv + pc.ct * t;
         y[row] = yv;
-        poly[row] += pc.cpu * uv + pc.cpy * yv;
+        poly[row] = e.pv + pc.cpu * e.uv + pc.cpy * yv;
       }
     }
   }
@@ -277,6 +294,8 @@ k_spmv_vel(DevMesh M, SpmvTiles TL, const VT* __restrict__ vals, const double* _
     if (A >= n1) break;
     const NodeDesc d = desc_from_smem(T, slot);
     const int nbd = DIM * d.nb, len = nbd + d.np;
+    EpiOps<DIM> eo;
+    vel_prefetch<DIM, MODE>(A, lane, u, poly, dinv, eo);
     const VT* rowp[DIM];
 #pragma unroll
     for (int c = 0; c < DIM; ++c) rowp[c] = vals + d.rowbase + (long long)c * len;
@@ -286,7 +305,7 @@ k_spmv_vel(DevMesh M, SpmvTiles TL, const VT* __restrict__ vals, const double* _
     tile_row_dot<DIM, DIM, VT>(rowp, nbd, nbd, T.idx + (d.nbr0 - T.base_n), nullptr, T.xs, 0, lane, sum);
 #pragma unroll
     for (int c = 0; c < DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
-    vel_epilogue<DIM, MODE>(A, lane, sum, y, u, poly, dinv, pc);
+    vel_epilogue<DIM, MODE>(A, lane, sum, y, poly, eo, pc);
   }
 }
 
@@ -316,6 +335,8 @@ k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __rest
     if (A >= n1) break;
     const NodeDesc d = desc_from_smem(T, slot);
     const int nbd = DIM * d.nb;
+    EpiOps<DIM> eo;
+    vel_prefetch<DIM, MODE>(A, lane, u, poly, dinv, eo);
     const V* rp = fv + (long long)DIM * d.nbr0;
     const unsigned short* nx = T.idx + (d.nbr0 - T.base_n);
     double sum[DIM];
@@ -340,7 +361,7 @@ k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __rest
     }
 #pragma unroll
     for (int c = 0; c < DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
-    vel_epilogue<DIM, MODE>(A, lane, sum, y, u, poly, dinv, pc);
+    vel_epilogue<DIM, MODE>(A, lane, sum, y, poly, eo, pc);
   }
 }
 

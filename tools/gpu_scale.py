@@ -53,8 +53,9 @@ def main():
     print(f"pressure matrices + AMG {time.time()-t0:.1f}s", flush=True)
     asm_bytes = 8 * nnz + 8 * nrows + 8 * 3 * 4 * nc + 20 * 34 * nc
     spmv_bytes = 12 * nnz + 16 * nrows + 4 * (nrows + 1)
-    sweeps = [dict(poly_target=0.12, poly_degree_F=64, poly_kind=1), dict(poly_target=0.16, poly_degree_F=64, poly_kind=1),
-              dict(poly_target=0.22, poly_degree_F=64, poly_kind=1), dict(poly_target=0.3, poly_degree_F=64, poly_kind=1)]
+    sweeps = [dict()]
+    if len(sys.argv) > 3:
+        sweeps = [dict(poly_target=t) for t in (0.05, 0.08, 0.12)]
     for deg in sweeps:
         dev.set_solver_opts(**deg)
         dev.profile_enable(True)
