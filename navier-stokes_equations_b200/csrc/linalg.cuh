@@ -317,6 +317,8 @@ k_spmv_vel(DevMesh M, SpmvTiles TL, const VT* __restrict__ vals, const double* _
 template <int DIM> struct F32Vec { using type = float4; };
 template <> struct F32Vec<2> { using type = float2; };
 
+constexpr int F32_UNROLL = 3;               // 3 x 32 columns covers the 81 columns of a line node in one trip
+
 template <int DIM, int MODE>
 __global__ void __launch_bounds__(SPMV_WARPS * 32)
 k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __restrict__ fv,
@@ -342,18 +344,18 @@ k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __rest
     double sum[DIM];
 #pragma unroll
     for (int c = 0; c < DIM; ++c) sum[c] = 0.0;
-    for (int k0 = 0; k0 < nbd; k0 += 32 * SPMV_UNROLL) {
-      V v[SPMV_UNROLL];
-      double xv[SPMV_UNROLL];
+    for (int k0 = 0; k0 < nbd; k0 += 32 * F32_UNROLL) {
+      V v[F32_UNROLL];
+      double xv[F32_UNROLL];
 #pragma unroll
-      for (int q = 0; q < SPMV_UNROLL; ++q) {
+      for (int q = 0; q < F32_UNROLL; ++q) {
         const int k = k0 + 32 * q + lane;
         v[q] = V();
         xv[q] = 0.0;
         if (k < nbd) { v[q] = __ldcs(rp + k); xv[q] = T.xs[(int)nx[k / DIM] * DIM + k % DIM]; }
       }
 #pragma unroll
-      for (int q = 0; q < SPMV_UNROLL; ++q) {
+      for (int q = 0; q < F32_UNROLL; ++q) {
         sum[0] += (double)v[q].x * xv[q];
         sum[1] += (double)v[q].y * xv[q];
         if (DIM == 3) sum[DIM - 1] += (double)reinterpret_cast<const float*>(&v[q])[DIM - 1] * xv[q];
