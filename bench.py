@@ -83,6 +83,16 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons}
 
 
+def recorded_traffic(level, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    (profiles/r01_traffic.json); None when no capture exists for this workload / kernel."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        return t[str(level)][kernel]
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -161,6 +171,12 @@ def main():
         if rank == 0:
             reference_arm(args, full_cells)
         return
+
+    # Everything but the final JSON line goes to stderr -- including what C libraries (NCCL's version
+    # banner) write to file descriptor 1.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     from tests.conftest import load_nsb
@@ -309,7 +325,7 @@ def main():
         if dom in kernels and bytes_alg.get(dom):
             ach = bytes_alg[dom] / (kernels[dom]["ms_avg"] * 1e-3) / 1e9
             line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_alg[dom])}
+                                "traffic": recorded_traffic(args.level, dom) if world == 1 else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_alg[dom])}
         for k in ("spmv", "asm_rows"):
             if k in kernels:
                 kernels[k]["algorithmic_GBps"] = round(bytes_alg[k] / (kernels[k]["ms_avg"] * 1e-3) / 1e9, 1)
@@ -319,7 +335,10 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": 1, "kind": "port",
                                     "sample": "oracle (numpy/scipy) step on a %d-cell mesh of the same geometry: %.1f s, %d GMRES its; "
                                               "scaled by cells to the %d-cell workload" % (cells_s, sec, its_s, hs.n_cells)}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     dev.close()
     if world > 1:
         dist.destroy_process_group()
