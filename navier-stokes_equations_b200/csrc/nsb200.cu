@@ -1579,6 +1579,43 @@ int nsb_test_build_pattern(int dim, int64_t n_vertices, const double* coords, in
   return 0;
 }
 
+/* halo plan of `rank`/`nranks` in GLOBAL DoF ids (two calls: first with NULL arrays for the sizes).
+ * ghost_gdof: global DoF of every ghost entry in local vector order [u_ghost | p_ghost];
+ * per peer k: send_u (velocity DoFs, node-major) / send_p (pressure DoFs) lists concatenated in peer order with
+ * prefix arrays send_u_ptr / send_p_ptr [n_peers+1]; recv_u_count / recv_p_count = entries received from peer k,
+ * which land contiguously, in peer order, in the u-ghost resp. p-ghost range. */
+int nsb_test_halo_plan(int dim, int64_t n_vertices, const double* coords, int64_t n_cells, const uint32_t* cell_vertices,
+                       const uint32_t* cell_dofs, int64_t n_u, int64_t n_p, const int32_t* cell_part, int rank, int nranks,
+                       int64_t* n_ghost, int64_t* ghost_gdof, int32_t* n_peers, int32_t* peers, int64_t* send_u_ptr,
+                       int64_t* send_u_gdof, int64_t* send_p_ptr, int64_t* send_p_gdof, int64_t* recv_u_count,
+                       int64_t* recv_p_count) {
+  Structure S;
+  const std::string e = build_structure(dim, n_vertices, coords, n_cells, cell_vertices, cell_dofs, n_u, n_p, cell_part, rank, nranks, S);
+  if (!e.empty()) { std::fprintf(stderr, "nsb_test_halo_plan: %s\n", e.c_str()); return -1; }
+  if (n_ghost) *n_ghost = S.n_tot_dofs() - S.n_own_dofs();
+  if (n_peers) *n_peers = (int32_t)S.peer.size();
+  if (ghost_gdof) {
+    int64_t k = 0;
+    for (int A = S.nn_own; A < S.nn_own + S.nn_ghost; ++A)
+      for (int c = 0; c < dim; ++c) ghost_gdof[k++] = S.node_gid[A] * dim + c;
+    for (int P = S.np_own; P < S.np_own + S.np_ghost; ++P) ghost_gdof[k++] = n_u + S.pid_gid[P];
+  }
+  int64_t su = 0, sp = 0;
+  for (size_t k = 0; k < S.peer.size(); ++k) {
+    if (peers) peers[k] = S.peer[k];
+    if (send_u_ptr) send_u_ptr[k] = su;
+    if (send_p_ptr) send_p_ptr[k] = sp;
+    for (int A : S.send_nodes[k])
+      for (int c = 0; c < dim; ++c) { if (send_u_gdof) send_u_gdof[su] = S.node_gid[A] * dim + c; ++su; }
+    for (int P : S.send_pids[k]) { if (send_p_gdof) send_p_gdof[sp] = n_u + S.pid_gid[P]; ++sp; }
+    if (recv_u_count) recv_u_count[k] = (int64_t)S.recv_node_count[k] * dim;
+    if (recv_p_count) recv_p_count[k] = S.recv_pid_count[k];
+  }
+  if (send_u_ptr) send_u_ptr[S.peer.size()] = su;
+  if (send_p_ptr) send_p_ptr[S.peer.size()] = sp;
+  return 0;
+}
+
 /* eigenvalues of an upper-Hessenberg matrix */
 int nsb_test_hessenberg_eigs(int n, const double* a, double* wr, double* wi) {
   std::vector<double> A(a, a + (size_t)n * n), r, i;
