@@ -317,39 +317,55 @@ k_spmv_vel(DevMesh M, SpmvTiles TL, const VT* __restrict__ vals, const double* _
 template <int DIM> struct F32Vec { using type = float4; };
 template <> struct F32Vec<2> { using type = float2; };
 
-constexpr int F32_UNROLL = 3;               // 3 x 32 columns covers the 81 columns of a line node in one trip
+// Sub-warp mapping: F32_SUB lanes per node, 32/F32_SUB nodes per warp at a time.  A line node has only
+// dim*27 = 81 columns, so with a whole warp per node the fixed per-node work (descriptor decode, shuffle
+// reduction, epilogue, slot fetch) outweighed the streaming loop; sharing one instruction stream between
+// four nodes divides that overhead by four and puts four nodes' loads in flight per warp.  `order` lists a
+// tile's nodes by decreasing row length so the nodes that share a warp have similar trip counts.
+constexpr int F32_SUB = 8;
+constexpr int F32_UNROLL = 3;
 
 template <int DIM, int MODE>
 __global__ void __launch_bounds__(SPMV_WARPS * 32)
-k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __restrict__ fv,
-               const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ u,
-               double* __restrict__ poly, const double* __restrict__ dinv, PolyCoef pc) {
+k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const unsigned char* __restrict__ order,
+               const typename F32Vec<DIM>::type* __restrict__ fv, const double* __restrict__ x, double* __restrict__ y,
+               const double* __restrict__ u, double* __restrict__ poly, const double* __restrict__ dinv, PolyCoef pc) {
   using V = typename F32Vec<DIM>::type;
+  constexpr int G = 32 / F32_SUB;
   __shared__ TileSmem<DIM> T;
   const int lane = threadIdx.x & 31;
+  const int sl = lane % F32_SUB, grp = lane / F32_SUB;
   int n0, n1;
   stage_tile<DIM, false>(M, TL, blockIdx.x, x, T, n0, n1);
+  const int nn = n1 - n0;
   for (;;) {
-    int slot = 0;
-    if (lane == 0) slot = atomicAdd(&T.next, 1);
-    slot = __shfl_sync(NSB_FULL, slot, 0);
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&T.next, G);
+    base = __shfl_sync(NSB_FULL, base, 0);
+    if (base >= nn) break;
+    const int slot_o = base + grp;
+    const bool have = slot_o < nn;
+    const int slot = have ? (int)__ldg(order + n0 + slot_o) : 0;
     const int A = n0 + slot;
-    if (A >= n1) break;
-    const NodeDesc d = desc_from_smem(T, slot);
-    const int nbd = DIM * d.nb;
+    const int4 b4 = T.desc[2 * slot + 1];
+    const int nbr0 = b4.x;
+    const int nbd = have ? DIM * (b4.z & 0xffff) : 0;
     EpiOps<DIM> eo;
-    vel_prefetch<DIM, MODE>(A, lane, u, poly, dinv, eo);
-    const V* rp = fv + (long long)DIM * d.nbr0;
-    const unsigned short* nx = T.idx + (d.nbr0 - T.base_n);
+    vel_prefetch<DIM, MODE>(A, have ? sl : DIM, u, poly, dinv, eo);
+    const V* rp = fv + (long long)DIM * nbr0;
+    const unsigned short* nx = T.idx + (nbr0 - T.base_n);
+    int nmax = nbd;
+#pragma unroll
+    for (int o = F32_SUB; o < 32; o <<= 1) nmax = max(nmax, __shfl_xor_sync(NSB_FULL, nmax, o));
     double sum[DIM];
 #pragma unroll
     for (int c = 0; c < DIM; ++c) sum[c] = 0.0;
-    for (int k0 = 0; k0 < nbd; k0 += 32 * F32_UNROLL) {
+    for (int k0 = 0; k0 < nmax; k0 += F32_SUB * F32_UNROLL) {
       V v[F32_UNROLL];
       double xv[F32_UNROLL];
 #pragma unroll
       for (int q = 0; q < F32_UNROLL; ++q) {
-        const int k = k0 + 32 * q + lane;
+        const int k = k0 + F32_SUB * q + sl;
         v[q] = V();
         xv[q] = 0.0;
         if (k < nbd) { v[q] = __ldcs(rp + k); xv[q] = T.xs[(int)nx[k / DIM] * DIM + k % DIM]; }
@@ -362,8 +378,10 @@ k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __rest
       }
     }
 #pragma unroll
-    for (int c = 0; c < DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
-    vel_epilogue<DIM, MODE>(A, lane, sum, y, poly, eo, pc);
+    for (int c = 0; c < DIM; ++c)
+#pragma unroll
+      for (int o = F32_SUB / 2; o > 0; o >>= 1) sum[c] += __shfl_xor_sync(NSB_FULL, sum[c], o);
+    if (have) vel_epilogue<DIM, MODE>(A, sl, sum, y, poly, eo, pc);
   }
 }
 

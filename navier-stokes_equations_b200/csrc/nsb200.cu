@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -192,6 +193,7 @@ struct nsb_ctx {
   int n_tiles = 0, tile_smem_bytes = 0;
   DBuf<int> d_stile_ptr, d_suniq_ptr, d_suniq_xoff, d_spuniq_ptr, d_spuniq_xoff;   // SpMV tiles (see linalg.cuh)
   DBuf<unsigned short> d_nbr_loc, d_pnbr_loc;
+  DBuf<unsigned char> d_sorder;     // per tile: node slots by decreasing row length (sub-warp SpMV)
   SpmvTiles stiles{};
   int n_stiles = 0;
   // global dof -> local vector offset (or -1)
@@ -352,8 +354,8 @@ void spmv_vel(nsb_ctx* c, const double* x, double* y, const double* u, double* p
   size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
   const int g = c->n_stiles;
   if (c->vals_f.p && MODE != 0) {
-    if (c->dim == 2) k_spmv_vel_f32<2, MODE><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float2*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
-    else k_spmv_vel_f32<3, MODE><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float4*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
+    if (c->dim == 2) k_spmv_vel_f32<2, MODE><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, c->d_sorder.p, reinterpret_cast<const float2*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
+    else k_spmv_vel_f32<3, MODE><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, c->d_sorder.p, reinterpret_cast<const float4*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
   } else {
     if (c->dim == 2) k_spmv_vel<2, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, c->vals.p, x, y, u, poly, c->dinv.p, pc);
     else k_spmv_vel<3, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, c->vals.p, x, y, u, poly, c->dinv.p, pc);
@@ -828,6 +830,7 @@ void build_tiles(nsb_ctx* c) {
     const int ntot = S.nn_own + S.nn_ghost, ptot = S.np_own + S.np_ghost;
     std::vector<int> sp, uptr, uxoff, pptr, pxoff;
     std::vector<unsigned short> nloc(S.nbr.size()), ploc(S.pnbr.size());
+    std::vector<unsigned char> sorder(S.nn_own);
     std::vector<int> stamp(ntot, -1), pstamp(ptot, -1), posn(ntot, 0), posp(ptot, 0);
     sp.push_back(0); uptr.push_back(0); pptr.push_back(0);
     int A = 0, tile = 0;
@@ -860,6 +863,14 @@ void build_tiles(nsb_ctx* c) {
         for (int64_t k = S.nbr_ptr[B]; k < S.nbr_ptr[B + 1]; ++k) nloc[k] = (unsigned short)posn[S.nbr[k]];
         for (int64_t k = S.pnbr_ptr[B]; k < S.pnbr_ptr[B + 1]; ++k) ploc[k] = (unsigned short)posp[S.pnbr[k]];
       }
+      {
+        std::vector<int> ord(A - start);
+        std::iota(ord.begin(), ord.end(), 0);
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
+          return (S.nbr_ptr[start + a + 1] - S.nbr_ptr[start + a]) > (S.nbr_ptr[start + b + 1] - S.nbr_ptr[start + b]);
+        });
+        for (int i = 0; i < A - start; ++i) sorder[start + i] = (unsigned char)ord[i];
+      }
       sp.push_back(A); uptr.push_back((int)uxoff.size()); pptr.push_back((int)pxoff.size());
       ++tile;
     }
@@ -868,6 +879,7 @@ void build_tiles(nsb_ctx* c) {
     c->d_suniq_ptr.upload(uptr, c->stream); c->d_suniq_xoff.upload(uxoff, c->stream);
     c->d_spuniq_ptr.upload(pptr, c->stream); c->d_spuniq_xoff.upload(pxoff, c->stream);
     c->d_nbr_loc.upload(nloc, c->stream); c->d_pnbr_loc.upload(ploc, c->stream);
+    c->d_sorder.upload(sorder, c->stream);
     CK(cudaStreamSynchronize(c->stream));
     c->stiles.node_ptr = c->d_stile_ptr.p;
     c->stiles.uniq_ptr = c->d_suniq_ptr.p; c->stiles.uniq_xoff = c->d_suniq_xoff.p;
