@@ -75,7 +75,6 @@ constexpr int TILE_MAX_NODES = 64;
 constexpr int TILE_MAX_IDX = 3072;       // staged 16-bit neighbour positions (velocity + pressure)
 constexpr int TILE_MAX_UNIQ = 768;       // unique neighbour nodes per tile
 constexpr int TILE_MAX_PUNIQ = 256;      // unique neighbour pressure DoFs per tile
-constexpr int TILE_MAX_STREAM_NB = 896;  // neighbour entries per tile whose fp32 values are bulk-staged (3-D: 43 KB)
 
 struct SpmvTiles {
   const int* node_ptr;                   // [n_tiles+1] node ranges
@@ -318,41 +317,7 @@ k_spmv_vel(DevMesh M, SpmvTiles TL, const VT* __restrict__ vals, const double* _
 template <int DIM> struct F32Vec { using type = float4; };
 template <> struct F32Vec<2> { using type = float2; };
 
-// ---- TMA bulk staging of a tile's value stream ------------------------------------------------
-// The fp32 copy of F is laid out so that the values of a tile's nodes form ONE contiguous range
-// (index dim*nbr0 + k): the CTA fetches it with 1-D bulk asynchronous copies (cp.async.bulk, completion on
-// an mbarrier) into shared memory while the other threads stage descriptors, indices and x.  DRAM sees long
-// sequential bursts, no LDG instructions are spent on the stream, and the copies of the CTAs resident on an
-// SM overlap each other's compute.  (Tried before: per-lane LDG.128 streaming at 512 B per warp request
-// reached 55 % of the copy bandwidth; 8-lane sub-warps with 128 B segments were slower still.)
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-
 constexpr int F32_UNROLL = 3;               // 3 x 32 columns covers the 81 columns of a line node in one trip
-constexpr unsigned BULK_PIECE = 16384;      // bytes per cp.async.bulk
 
 template <int DIM, int MODE>
 __global__ void __launch_bounds__(SPMV_WARPS * 32)
@@ -360,28 +325,10 @@ k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __rest
                const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ u,
                double* __restrict__ poly, const double* __restrict__ dinv, PolyCoef pc) {
   using V = typename F32Vec<DIM>::type;
-  extern __shared__ __align__(128) unsigned char dyn_stream[];      // the tile's value stream
   __shared__ TileSmem<DIM> T;
-  __shared__ __align__(8) uint64_t bar;
   const int lane = threadIdx.x & 31;
-  // the stream range is known from the first / last descriptor: read them directly (2 x 16 B)
-  const int t = blockIdx.x;
-  const int tn0 = TL.node_ptr[t], tn1 = TL.node_ptr[t + 1];
-  if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
-    const int4 f = __ldg(reinterpret_cast<const int4*>(M.nd + tn0) + 1);
-    const int4 l = __ldg(reinterpret_cast<const int4*>(M.nd + (tn1 - 1)) + 1);
-    const long long first = (long long)DIM * f.x;
-    const unsigned bytes = (unsigned)((long long)DIM * (l.x + (l.z & 0xffff) - f.x) * (long long)sizeof(V));
-    mbar_expect_tx(&bar, bytes);
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(fv + first);
-    for (unsigned off = 0; off < bytes; off += BULK_PIECE)
-      bulk_g2s(dyn_stream + off, src + off, min(BULK_PIECE, bytes - off), &bar);
-  }
   int n0, n1;
-  stage_tile<DIM, false>(M, TL, t, x, T, n0, n1);          // contains __syncthreads(): publishes the barrier init
-  mbar_wait(&bar, 0);
-  const V* sv = reinterpret_cast<const V*>(dyn_stream);
+  stage_tile<DIM, false>(M, TL, blockIdx.x, x, T, n0, n1);
   for (;;) {
     int slot = 0;
     if (lane == 0) slot = atomicAdd(&T.next, 1);
@@ -392,22 +339,26 @@ k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __rest
     const int nbd = DIM * d.nb;
     EpiOps<DIM> eo;
     vel_prefetch<DIM, MODE>(A, lane, u, poly, dinv, eo);
-    const V* rp = sv + DIM * (d.nbr0 - T.base_n);
+    const V* rp = fv + (long long)DIM * d.nbr0;
     const unsigned short* nx = T.idx + (d.nbr0 - T.base_n);
     double sum[DIM];
 #pragma unroll
     for (int c = 0; c < DIM; ++c) sum[c] = 0.0;
     for (int k0 = 0; k0 < nbd; k0 += 32 * F32_UNROLL) {
+      V v[F32_UNROLL];
+      double xv[F32_UNROLL];
 #pragma unroll
       for (int q = 0; q < F32_UNROLL; ++q) {
         const int k = k0 + 32 * q + lane;
-        if (k < nbd) {
-          const V v = rp[k];
-          const double xv = T.xs[(int)nx[k / DIM] * DIM + k % DIM];
-          sum[0] += (double)v.x * xv;
-          sum[1] += (double)v.y * xv;
-          if (DIM == 3) sum[DIM - 1] += (double)reinterpret_cast<const float*>(&v)[DIM - 1] * xv;
-        }
+        v[q] = V();
+        xv[q] = 0.0;
+        if (k < nbd) { v[q] = __ldcs(rp + k); xv[q] = T.xs[(int)nx[k / DIM] * DIM + k % DIM]; }
+      }
+#pragma unroll
+      for (int q = 0; q < F32_UNROLL; ++q) {
+        sum[0] += (double)v[q].x * xv[q];
+        sum[1] += (double)v[q].y * xv[q];
+        if (DIM == 3) sum[DIM - 1] += (double)reinterpret_cast<const float*>(&v[q])[DIM - 1] * xv[q];
       }
     }
 #pragma unroll

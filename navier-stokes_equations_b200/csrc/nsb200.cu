@@ -12,7 +12,6 @@
 #include <cstring>
 #include <map>
 #include <memory>
-#include <numeric>
 #include <string>
 #include <vector>
 
@@ -193,9 +192,8 @@ struct nsb_ctx {
   int n_tiles = 0, tile_smem_bytes = 0;
   DBuf<int> d_stile_ptr, d_suniq_ptr, d_suniq_xoff, d_spuniq_ptr, d_spuniq_xoff;   // SpMV tiles (see linalg.cuh)
   DBuf<unsigned short> d_nbr_loc, d_pnbr_loc;
-  DBuf<unsigned char> d_sorder;     // per tile: node slots by decreasing row length (sub-warp SpMV)
   SpmvTiles stiles{};
-  int n_stiles = 0, stile_stream_bytes = 0;    // dynamic shared memory of k_spmv_vel_f32: largest tile value stream
+  int n_stiles = 0;
   // global dof -> local vector offset (or -1)
   std::vector<int> g2x;
   DBuf<int> d_pid_gid;              // [np_own] global pressure id of each owned pressure DoF (multi-GPU)
@@ -335,16 +333,6 @@ template <int DIM> void launch_assemble(nsb_ctx* c, bool newton) {
   c->prof.end(id, c->stream);
 }
 
-void set_stream_smem_attr(int dim, int bytes) {
-  if (dim == 2) {
-    CK(cudaFuncSetAttribute(k_spmv_vel_f32<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_spmv_vel_f32<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  } else {
-    CK(cudaFuncSetAttribute(k_spmv_vel_f32<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_spmv_vel_f32<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  }
-}
-
 template <int DIM> void set_smem_attr(int bytes) {
   CK(cudaFuncSetAttribute(k_node_rows<DIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute(k_node_rows<DIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -364,8 +352,8 @@ void spmv_vel(nsb_ctx* c, const double* x, double* y, const double* u, double* p
   size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
   const int g = c->n_stiles;
   if (c->vals_f.p && MODE != 0) {
-    if (c->dim == 2) k_spmv_vel_f32<2, MODE><<<g, SPMV_WARPS * 32, c->stile_stream_bytes, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float2*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
-    else k_spmv_vel_f32<3, MODE><<<g, SPMV_WARPS * 32, c->stile_stream_bytes, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float4*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
+    if (c->dim == 2) k_spmv_vel_f32<2, MODE><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float2*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
+    else k_spmv_vel_f32<3, MODE><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float4*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
   } else {
     if (c->dim == 2) k_spmv_vel<2, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, c->vals.p, x, y, u, poly, c->dinv.p, pc);
     else k_spmv_vel<3, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, c->vals.p, x, y, u, poly, c->dinv.p, pc);
@@ -840,20 +828,19 @@ void build_tiles(nsb_ctx* c) {
     const int ntot = S.nn_own + S.nn_ghost, ptot = S.np_own + S.np_ghost;
     std::vector<int> sp, uptr, uxoff, pptr, pxoff;
     std::vector<unsigned short> nloc(S.nbr.size()), ploc(S.pnbr.size());
-    std::vector<unsigned char> sorder(S.nn_own);
     std::vector<int> stamp(ntot, -1), pstamp(ptot, -1), posn(ntot, 0), posp(ptot, 0);
     sp.push_back(0); uptr.push_back(0); pptr.push_back(0);
-    int A = 0, tile = 0, max_stream_nb = 0;
+    int A = 0, tile = 0;
     std::vector<int> U, PU;
     while (A < S.nn_own) {
       U.clear(); PU.clear();
-      int idx = 0, cn = 0, stream_nb = 0;
+      int idx = 0, cn = 0;
       const int start = A;
       while (A < S.nn_own && cn < TILE_MAX_NODES) {
         const int nb = (int)(S.nbr_ptr[A + 1] - S.nbr_ptr[A]), np = (int)(S.pnbr_ptr[A + 1] - S.pnbr_ptr[A]);
         if (nb + np > TILE_MAX_IDX || nb > TILE_MAX_UNIQ || np > TILE_MAX_PUNIQ)
           throw CudaErr{"a node has more neighbours than one SpMV tile can stage"};
-        if (idx + nb + np > TILE_MAX_IDX || (cn > 0 && stream_nb + nb > TILE_MAX_STREAM_NB)) break;
+        if (idx + nb + np > TILE_MAX_IDX) break;
         int newu = 0, newp = 0;
         for (int64_t k = S.nbr_ptr[A]; k < S.nbr_ptr[A + 1]; ++k) newu += stamp[S.nbr[k]] != tile;
         for (int64_t k = S.pnbr_ptr[A]; k < S.pnbr_ptr[A + 1]; ++k) newp += pstamp[S.pnbr[k]] != tile;
@@ -862,7 +849,7 @@ void build_tiles(nsb_ctx* c) {
           if (stamp[S.nbr[k]] != tile) { stamp[S.nbr[k]] = tile; U.push_back(S.nbr[k]); }
         for (int64_t k = S.pnbr_ptr[A]; k < S.pnbr_ptr[A + 1]; ++k)
           if (pstamp[S.pnbr[k]] != tile) { pstamp[S.pnbr[k]] = tile; PU.push_back(S.pnbr[k]); }
-        idx += nb + np; stream_nb += nb; ++cn; ++A;
+        idx += nb + np; ++cn; ++A;
       }
       // memory order, then positions
       std::sort(U.begin(), U.end(), [&](int a, int b) { return S.node_xoff(a) < S.node_xoff(b); });
@@ -873,26 +860,14 @@ void build_tiles(nsb_ctx* c) {
         for (int64_t k = S.nbr_ptr[B]; k < S.nbr_ptr[B + 1]; ++k) nloc[k] = (unsigned short)posn[S.nbr[k]];
         for (int64_t k = S.pnbr_ptr[B]; k < S.pnbr_ptr[B + 1]; ++k) ploc[k] = (unsigned short)posp[S.pnbr[k]];
       }
-      max_stream_nb = std::max(max_stream_nb, stream_nb);
-      {
-        std::vector<int> ord(A - start);
-        std::iota(ord.begin(), ord.end(), 0);
-        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
-          return (S.nbr_ptr[start + a + 1] - S.nbr_ptr[start + a]) > (S.nbr_ptr[start + b + 1] - S.nbr_ptr[start + b]);
-        });
-        for (int i = 0; i < A - start; ++i) sorder[start + i] = (unsigned char)ord[i];
-      }
       sp.push_back(A); uptr.push_back((int)uxoff.size()); pptr.push_back((int)pxoff.size());
       ++tile;
     }
     c->n_stiles = (int)sp.size() - 1;
-    c->stile_stream_bytes = max_stream_nb * S.dim * (S.dim == 3 ? 16 : 8);
-    set_stream_smem_attr(c->dim, c->stile_stream_bytes);
     c->d_stile_ptr.upload(sp, c->stream);
     c->d_suniq_ptr.upload(uptr, c->stream); c->d_suniq_xoff.upload(uxoff, c->stream);
     c->d_spuniq_ptr.upload(pptr, c->stream); c->d_spuniq_xoff.upload(pxoff, c->stream);
     c->d_nbr_loc.upload(nloc, c->stream); c->d_pnbr_loc.upload(ploc, c->stream);
-    c->d_sorder.upload(sorder, c->stream);
     CK(cudaStreamSynchronize(c->stream));
     c->stiles.node_ptr = c->d_stile_ptr.p;
     c->stiles.uniq_ptr = c->d_suniq_ptr.p; c->stiles.uniq_xoff = c->d_suniq_xoff.p;
