@@ -273,3 +273,45 @@ def test_full_size_properties_mesh_3d_10(nsb):
     xs = dev.get_vector(nsb.NSB_SOLUTION)
     assert np.array_equal(xs[con.is_c], con.val[con.is_c])
     dev.close()
+
+
+def test_solver_options_reach_the_same_solution(case3d):
+    """fp64 vs fp32 operator inside the velocity polynomial, Chebyshev vs harmonic-Ritz roots, the reference's
+    theta*nu Schur scaling: different preconditioners, same linear system => same tight-tolerance solution."""
+    c = case3d
+    nsb = c.nsb
+    con = c.constraints()
+    c.linearized(0.5, False, con)
+    c.dev.assemble_pressure_matrices()
+    ok, it0, _ = c.dev.solve(3000, 1e-12, 150)
+    x0 = c.dev.get_vector(nsb.NSB_SOLUTION)
+    assert ok
+    for opts in (dict(precond_precision=64), dict(poly_kind=-1), dict(poly_target=0.2, poly_degree_F=8),
+                 dict(schur_mass_coeff=0.5 * c.nu)):
+        c.dev.set_solver_opts(**opts)
+        c.dev.assemble_linearized()            # refills the operator copy after a precision change
+        ok, it, _ = c.dev.solve(3000, 1e-12, 150)
+        x = c.dev.get_vector(nsb.NSB_SOLUTION)
+        assert ok, opts
+        assert np.linalg.norm(x - x0) / np.linalg.norm(x0) < 1e-9, opts
+    c.dev.set_solver_opts()
+    c.dev.assemble_linearized()
+    info = c.dev.solver_info()
+    assert info["amg_levels"] >= 1 and info["poly_degree"] >= 1
+
+
+def test_host_class_newton_3d1z_step_matches_oracle(nsb, small_3d_mesh, tmp_path):
+    """3D-1Z: backward Euler + Newton with SUPG (strong residual incl. the P2 Laplacian) and grad-div."""
+    path = str(tmp_path / "m3.bin")
+    msh.write_bin(path, small_3d_mesh)
+    s = nsb.HostSolver("3D-1Z", path, gmres_tolerance=1e-12)
+    s.initialize()
+    info = s.step()
+    o = osolve.Oracle(small_3d_mesh, "3D-1Z", solver="direct")
+    ref = o.step()
+    assert info["newton_iterations"] == ref["newton_iters"]
+    for key in ("cd", "cl", "dp"):
+        assert abs(info[key] - ref[key]) <= TOL_FORCE * abs(ref[key]) + 1e-12, (key, info[key], ref[key])
+    x = s.solution()
+    assert np.linalg.norm(x - o.current_solution) / np.linalg.norm(o.current_solution) < TOL_FIELD
+    s.close()

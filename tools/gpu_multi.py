@@ -72,6 +72,26 @@ def main():
     print(out, flush=True)
     dist.barrier()
     dev.close()
+    # ---- the C++ host class NavierStokes<3>(make_3D_2Z) on `world` GPUs: three time steps in parity mode
+    from tools import msh
+    path = "/tmp/gpu_multi_mesh_%d.bin" % rank
+    msh.write_bin(path, mesh)
+    holder3 = [nsb.Device.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(holder3, src=0)
+    hs = nsb.HostSolver("3D-2Z", path, device=local, rank=rank, nranks=world, nccl_unique_id=holder3[0], gmres_tolerance=1e-12)
+    hs.initialize()
+    infos = [hs.step() for _ in range(3)]
+    if rank == 0:
+        o = osolve.Oracle(mesh, "3D-2Z", solver="direct")
+        for k, info in enumerate(infos):
+            ref_ = o.step()
+            errs = {key: abs(info[key] - ref_[key]) / max(abs(ref_[key]), 1e-300) for key in ("cd", "cl", "dp")}
+            print(f"[host class, {world} GPUs] step {k + 1}: gmres {info['gmres_iterations']} its, rel err vs oracle "
+                  + ", ".join(f"{a}={b:.1e}" for a, b in errs.items()) + f"  (Cd={info['cd']:.6g} Cl={info['cl']:.3g} dP={info['dp']:.6g})", flush=True)
+        x = hs.solution()
+        print(f"[host class, {world} GPUs] field rel L2 vs oracle after 3 steps: {np.linalg.norm(x - o.current_solution) / np.linalg.norm(o.current_solution):.2e}", flush=True)
+    dist.barrier()
+    hs.close()
     dist.destroy_process_group()
 
 
