@@ -9,9 +9,16 @@
 #pragma once
 #include "device.cuh"
 
+#ifndef NSB_STREAM_LOAD
+#define NSB_STREAM_LOAD __ldcs
+#endif
+
 namespace nsb {
 
-constexpr int SPMV_WARPS = 8;
+#ifndef NSB_SPMV_WARPS
+#define NSB_SPMV_WARPS 8
+#endif
+constexpr int SPMV_WARPS = NSB_SPMV_WARPS;
 
 // ------------------------------------------------------------------------------------
 // Row kernels over the node-block structure.  One warp per owned P2 node handles the node's
@@ -71,7 +78,10 @@ __device__ __forceinline__ void row_block_dot(const VT* const (&rowp)[ROWS], int
 // and only stream matrix values; the x "gather" happens in shared memory.  This is what takes
 // the scattered 8-byte gathers -- which saturated L1/TEX at ~12 wavefronts per request -- out
 // of the inner loop.
-constexpr int TILE_MAX_NODES = 64;
+#ifndef NSB_TILE_NODES
+#define NSB_TILE_NODES 64
+#endif
+constexpr int TILE_MAX_NODES = NSB_TILE_NODES;
 constexpr int TILE_MAX_IDX = 3072;       // staged 16-bit neighbour positions (velocity + pressure)
 constexpr int TILE_MAX_UNIQ = 768;       // unique neighbour nodes per tile
 constexpr int TILE_MAX_PUNIQ = 256;      // unique neighbour pressure DoFs per tile
@@ -317,7 +327,10 @@ k_spmv_vel(DevMesh M, SpmvTiles TL, const VT* __restrict__ vals, const double* _
 template <int DIM> struct F32Vec { using type = float4; };
 template <> struct F32Vec<2> { using type = float2; };
 
-constexpr int F32_UNROLL = 3;               // 3 x 32 columns covers the 81 columns of a line node in one trip
+#ifndef NSB_F32_UNROLL
+#define NSB_F32_UNROLL 3
+#endif
+constexpr int F32_UNROLL = NSB_F32_UNROLL;  // 3 x 32 columns covers the 81 columns of a line node in one trip
 
 template <int DIM, int MODE>
 __global__ void __launch_bounds__(SPMV_WARPS * 32)
@@ -352,7 +365,7 @@ k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __rest
         const int k = k0 + 32 * q + lane;
         v[q] = V();
         xv[q] = 0.0;
-        if (k < nbd) { v[q] = __ldcs(rp + k); xv[q] = T.xs[(int)nx[k / DIM] * DIM + k % DIM]; }
+        if (k < nbd) { v[q] = NSB_STREAM_LOAD(rp + k); xv[q] = T.xs[(int)nx[k / DIM] * DIM + k % DIM]; }
       }
 #pragma unroll
       for (int q = 0; q < F32_UNROLL; ++q) {

@@ -17,32 +17,25 @@ def main():
     level = int(sys.argv[1]) if len(sys.argv) > 1 else 10
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     nsb = load_nsb()
+    import bench
     t0 = time.time()
-    mesh = meshgen.mesh_3d(level)
-    print(f"mesh-3D-{level}: cells {mesh.n_cells} vertices {mesh.n_vertices}  gen {time.time()-t0:.1f}s", flush=True)
-    t0 = time.time()
-    dm = odofs.enumerate_dofs(mesh)
-    print(f"dofs {dm.n_u}+{dm.n_p}  enumerate {time.time()-t0:.1f}s", flush=True)
-    N = dm.n_dofs
+    mesh_file = bench.get_mesh_file(level)
+    hs = nsb.HostSetup(mesh_file, 3)
+    pts, cells = hs.mesh()
+    cell_dofs = hs.cell_dofs()
+    sp_pts, comp = hs.support_points()
+    cd, cvals = hs.constraints("3D-2Z", 1.0)
+    N = hs.n_dofs
+    print(f"mesh-3D-{level}: cells {hs.n_cells} dofs {hs.n_u}+{hs.n_p}  host setup {time.time()-t0:.1f}s  lib {os.path.basename(nsb.LIB_PATH)}", flush=True)
     tc = pp.TEST_CASES["3D-2Z"]
     dev = nsb.Device(3)
     t0 = time.time()
-    dev.upload_mesh(mesh.points, mesh.cells, dm.cell_dofs, dm.n_u, dm.n_p)
+    dev.upload_mesh(pts, cells, cell_dofs, hs.n_u, hs.n_p)
     nrows, nnz, nc = dev.sizes()
     print(f"upload_mesh {time.time()-t0:.1f}s  rows {nrows} nnz {nnz} ({nnz/nrows:.1f}/row)", flush=True)
-    ids = pp.boundary_ids(3)
     nu = pp.viscosity(3, tc["U_m"], tc["Re"])
-    inlet = pp.inlet_profile(3, tc["U_m"], tc["time_dep"], tc["T_ramp"], 1.0)
-    t0 = time.time()
-    con = odofs.build_constraints(mesh, dm, inlet, ids)
-    cd = con.dofs
-    dev.set_constraints(cd, con.val[cd])
-    print(f"constraints {cd.size} {time.time()-t0:.1f}s", flush=True)
-    full = pp.inlet_profile(3, tc["U_m"], False, 0.0, 0.0)
-    base = np.zeros(N)
-    base[:dm.n_u] = full(dm.support_points[:dm.n_u], dm.component[:dm.n_u])
-    un = base * (1 + 0.1 * np.random.default_rng(1234).uniform(-1, 1, N))
-    unm1 = base * (1 + 0.1 * np.random.default_rng(1235).uniform(-1, 1, N))
+    dev.set_constraints(cd, cvals)
+    un, unm1 = bench.synthetic_state(sp_pts, comp, hs.n_u)
     dev.set_params(0.01, 0.5, nu, 1.0, 0.1, True, False)
     dev.set_vector(nsb.NSB_SOLUTION_OLD, un)
     dev.set_vector(nsb.NSB_SOLUTION_OLD_OLD, unm1)
