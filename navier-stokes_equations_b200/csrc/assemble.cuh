@@ -84,7 +84,7 @@ k_cell_context(DevMesh M, AsmParams P, const FeTables* __restrict__ gT, const do
   for (int v = 0; v < NV; ++v)
 #pragma unroll
     for (int k = 0; k < DIM; ++k) gl[v][k] = __ldg(geo + v * DIM + k);
-  const double absJ = __ldg(geo + 12), h = __ldg(geo + 13);
+  const double absJ = __ldg(geo + 12), inv_h = __ldg(geo + 14);
   if (lane < NN * DIM) {
     const int a = lane / DIM, c = lane % DIM;
     const int xo = __ldg(M.cell_xoff + (size_t)cell * NN + a) + c;
@@ -152,7 +152,7 @@ k_cell_context(DevMesh M, AsmParams P, const FeTables* __restrict__ gT, const do
 #pragma unroll
       for (int c = 0; c < DIM; ++c) um += ustar[c] * ustar[c];
       um = sqrt(um);
-      const double t1 = 2.0 / P.dt, t2 = 2.0 * um / h, t3 = 4.0 * P.nu / (h * h);
+      const double t1 = 2.0 * P.inv_dt, t2 = 2.0 * um * inv_h, t3 = 4.0 * P.nu * inv_h * inv_h;
       tw = JxW / sqrt(t1 * t1 + t2 * t2 + t3 * t3);      // tau * JxW   (cpp:727-729)
     }
     double* o = sq + q * Q::N;
@@ -178,14 +178,14 @@ k_cell_context(DevMesh M, AsmParams P, const FeTables* __restrict__ gT, const do
       // rhs of the linearised system (cpp:702-745)
 #pragma unroll
       for (int c = 0; c < DIM; ++c) {
-        o[Q::M + c] = JxW * ((1.0 / P.dt) * ua[c] - (1.0 - P.theta) * convA[c]);
+        o[Q::M + c] = JxW * (P.inv_dt * ua[c] - (1.0 - P.theta) * convA[c]);
         const double E = tw * ustar[c];                    // tau u*_c JxW: first-index contraction, cpp:733
 #pragma unroll
         for (int m = 0; m < NV; ++m) {
           double gg = 0, z = 0;
 #pragma unroll
           for (int k = 0; k < DIM; ++k) { gg += gl[m][k] * gA[c][k]; z += gl[m][k] * ua[k]; }
-          o[Q::WZ + c * NV + m] = -JxW * (1.0 - P.theta) * P.nu * gg + E * (z / P.dt);
+          o[Q::WZ + c * NV + m] = -JxW * (1.0 - P.theta) * P.nu * gg + E * (z * P.inv_dt);
         }
       }
     } else {
@@ -213,8 +213,8 @@ k_cell_context(DevMesh M, AsmParams P, const FeTables* __restrict__ gT, const do
 #pragma unroll
       for (int c = 0; c < DIM; ++c) {
         tr += gA[c][c];
-        o[Q::M + c] = -JxW * ((ua[c] - ub[c]) / P.dt + P.theta * convA[c] + (1.0 - P.theta) * convB[c]);
-        const double strong = (ua[c] - ub[c]) / P.dt + convA[c] + gp[c] - P.nu * lap[c];
+        o[Q::M + c] = -JxW * ((ua[c] - ub[c]) * P.inv_dt + P.theta * convA[c] + (1.0 - P.theta) * convB[c]);
+        const double strong = (ua[c] - ub[c]) * P.inv_dt + convA[c] + gp[c] - P.nu * lap[c];
 #pragma unroll
         for (int m = 0; m < NV; ++m) {
           double ga = 0, gb = 0;
@@ -243,7 +243,7 @@ k_cell_context(DevMesh M, AsmParams P, const FeTables* __restrict__ gT, const do
       r += ph * o[Q::M + c] + d0 * o[Q::WZ + c * NV + ia] + d1 * o[Q::WZ + c * NV + ja];
       const double ca = d0 * o[Q::S + ia] + d1 * o[Q::S + ja];
       const double Pa = o[Q::JW] * P.theta * ph, Qa = o[Q::TW] * ca;
-      svar += Pa * ca + Qa * (ph / P.dt + ca);
+      svar += Pa * ca + Qa * (ph * P.inv_dt + ca);
       if (NEWTON) tnew += (Pa + Qa) * ph * o[Q::HH + c * DIM + c];
     }
     cell_rhs[(size_t)cell * DPC + lane] = r;
@@ -257,7 +257,7 @@ k_cell_context(DevMesh M, AsmParams P, const FeTables* __restrict__ gT, const do
       trG += g;
       if (k == c) Gcc = g;
     }
-    const double Saa = absJ * T.Mhat[a][a] / P.dt + P.theta * P.nu * trG + svar;
+    const double Saa = absJ * T.Mhat[a][a] * P.inv_dt + P.theta * P.nu * trG + svar;
     diag_abs = fabs(Saa + P.gamma * Gcc + tnew);
   }
   if (lane < NV) {
@@ -438,7 +438,7 @@ k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double
           const double cb = db0[t] * s[ib0] + db1[t] * s[ib1];
           const double Pa = T.w[q] * absJ * P.theta * pha;
           const double Qa = tw * ca;
-          part += Pa * cb + Qa * (phb[t] / P.dt + cb);
+          part += Pa * cb + Qa * (phb[t] * P.inv_dt + cb);
           capart += Qa;
         }
       }
@@ -458,7 +458,7 @@ k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double
       double trG = 0.0;
 #pragma unroll
       for (int k = 0; k < DIM; ++k) trG += shfl_d(Gdd, grp + k);
-      const double Sab = absJ * T.Mhat[a][b] / P.dt + P.theta * P.nu * trG + Svar;
+      const double Sab = absJ * T.Mhat[a][b] * P.inv_dt + P.theta * P.nu * trG + Svar;
       double val[DIM];
 #pragma unroll
       for (int c = 0; c < DIM; ++c) val[c] = P.gamma * G[c] + ((c == d) ? Sab : 0.0);

@@ -49,6 +49,7 @@ struct DevMesh {
 // reference NavierStokes.hpp:485-511 / cpp:660-676: everything assembly needs per call
 struct AsmParams {
   double dt, theta, nu, rho, gamma;     // gamma = 0.1 grad-div weight (cpp:463,793), 0 when !use_supg
+  double inv_dt;                        // 1/dt, computed once on the host (fp64 division is ~25 instructions on the device)
   int use_supg;
   int first_order_ustar;                // first_step || second_step || BackwardEuler (cpp:665)
 };

@@ -304,7 +304,7 @@ void allreduce_sum(nsb_ctx* c, double* dbuf, int n) {
 // ---- templated launch helpers --------------------------------------------------------
 template <int DIM> void launch_assemble(nsb_ctx* c, bool newton) {
   AsmParams P;
-  P.dt = c->par.dt; P.theta = c->par.theta; P.nu = c->par.nu; P.rho = c->par.rho;
+  P.dt = c->par.dt; P.inv_dt = 1.0 / c->par.dt; P.theta = c->par.theta; P.nu = c->par.nu; P.rho = c->par.rho;
   P.use_supg = c->par.use_supg;
   P.gamma = c->par.use_supg ? c->par.gamma : 0.0;
   P.first_order_ustar = c->par.first_order_ustar;

@@ -310,6 +310,7 @@ std::string build_structure(int dim, int64_t n_vertices, const double* coords, i
       for (int k = 0; k < dim; ++k) g[v * dim + k] = gl[v][k];
     g[12] = det;
     g[13] = h;
+    g[14] = 1.0 / h;
   }
   if (negative) return "mesh has cells with non-positive measure";
   (void)n_vertices;
