@@ -129,6 +129,19 @@ def make_sparsity(dm: DofMap):
     return rowptr, cols
 
 
+def make_sparsity_fast(dm: DofMap):
+    """Same pattern as make_sparsity, as the structure of G^T G for the cell-dof incidence matrix G
+    (seconds instead of a minute on 5e4 tets; tests/test_oracle_pins.py checks both agree)."""
+    import scipy.sparse as sp
+    N = dm.n_dofs
+    C, K = dm.cell_dofs.shape
+    G = sp.csr_matrix((np.ones(C * K, dtype=np.float32), dm.cell_dofs.ravel().astype(np.int64),
+                       np.arange(0, C * K + 1, K, dtype=np.int64)), shape=(C, N))
+    P = sp.csr_matrix(G.T @ G)
+    P.sort_indices()
+    return P.indptr.astype(np.int64), P.indices.astype(np.int32)
+
+
 def boundary_dofs(mesh, dm: DofMap, boundary_id, velocity=True, pressure=False):
     """DoFs located on boundary faces with the given id (vertices and lines of the face),
     restricted to the component mask -- the index set interpolate_boundary_values touches."""
