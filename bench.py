@@ -174,6 +174,8 @@ def main():
     ap.add_argument("--level", type=int, default=20, help="mesh-3D-<level>-equivalent (5, 10, 20, 40)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--operator", type=int, default=0,
+                    help="operator inside the velocity polynomial: 1 assembled fp32 copy, 2 element-wise, 0 library default")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -222,6 +224,8 @@ def main():
     n_u, n_p, N = hs.n_u, hs.n_p, hs.n_dofs
     log("[bench] rank %d host setup %.1f s: %d cells, %d + %d DoFs" % (rank, time.time() - t0, hs.n_cells, n_u, n_p))
     dev = nsb.Device(3, local_rank)
+    if args.operator:
+        dev.set_solver_opts(precond_operator=args.operator)
     part = None
     if world > 1:
         dev.comm_init(rank, world, uid)
@@ -310,6 +314,7 @@ def main():
         tot = {k: v[0] for k, v in prof.items()}
         dom = max(("spmv_vel", "spmv", "asm_rows", "orth"), key=lambda k: tot.get(k, 0.0))
         blocks = dev.block_nnz()
+        opts_eff = dev.get_solver_opts()
         bytes_alg = {
             "spmv": 12 * nnz + 16 * nrows + 4 * (nrows + 1),
             "spmv_vel": None,
@@ -327,7 +332,9 @@ def main():
                                    "SUPG+grad-div, GMRES(150) tol 1e-2*||b||, max 200 its" % (args.level, hs.n_cells, N, nnz),
                        "parallelism": "1 process per GPU, contiguous cell chunks" if world > 1 else "single GPU",
                        "l2": "inputs (%.1f GB of matrix values) exceed L2; no flush needed" % (8e-9 * nnz),
-                       "gmres_iterations_per_step": iters, "solver": dev.solver_info()},
+                       "gmres_iterations_per_step": iters,
+                       "solver": dict(dev.solver_info(), velocity_operator={1: "assembled fp%d copy" % opts_eff["precond_precision"],
+                                                                            2: "element-wise (S rows fp32 + cell geometry)"}[opts_eff["precond_operator"]])},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": int(2 * 8 * N + 12 * cdofs.size),
@@ -339,7 +346,7 @@ def main():
         if dom in kernels and bytes_alg.get(dom):
             ach = bytes_alg[dom] / (kernels[dom]["ms_avg"] * 1e-3) / 1e9
             line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                "traffic": recorded_traffic(args.level, dom) if world == 1 else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_alg[dom])}
+                                "traffic": recorded_traffic(args.level, dom + ("_ebe" if dom == "spmv_vel" and opts_eff["precond_operator"] == 2 else "")) if world == 1 else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_alg[dom])}
         for k in ("spmv", "asm_rows"):
             if k in kernels:
                 kernels[k]["algorithmic_GBps"] = round(bytes_alg[k] / (kernels[k]["ms_avg"] * 1e-3) / 1e9, 1)

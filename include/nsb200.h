@@ -53,6 +53,10 @@ typedef struct nsb_solver_opts {
   int32_t precond_precision;/* storage of the operator used INSIDE the velocity polynomial: 32 (default; products are
                                accumulated in fp64, so the preconditioner stays a fixed linear operator) or 64.
                                Changing it invalidates the assembled system (re-assemble before solving). */
+  int32_t precond_operator; /* how that operator is applied: 1 = from an assembled copy of the velocity block (precision above);
+                               2 = element-wise from per-cell rows S_e[a][:] (fp32) + the cell geometry, 2.4x fewer bytes
+                               per application; linearised systems only, Newton systems use the assembled fp64 values.
+                               0 = library default.  Changing it invalidates the assembled system. */
 } nsb_solver_opts;
 
 /* ---- lifetime -------------------------------------------------------------------- */
@@ -92,6 +96,8 @@ int nsb_get_row_gids(nsb_handle h, int64_t* gid);
 int nsb_set_constraints(nsb_handle h, int64_t n, const uint32_t* dof, const double* val);
 int nsb_set_params(nsb_handle h, const nsb_params* p);
 int nsb_set_solver_opts(nsb_handle h, const nsb_solver_opts* o);
+/* the options in effect (defaults resolved) */
+int nsb_get_solver_opts(nsb_handle h, nsb_solver_opts* out);
 
 enum {
   NSB_SOLUTION_OLD = 0,      /* solution_old        u^n                (hpp:578)           */
@@ -134,6 +140,9 @@ int nsb_get_pressure_matrix(nsb_handle h, int which /*0 Mp, 1 Kp*/, int64_t* n, 
                             int32_t* rowptr, int32_t* col, double* val);
 /* y = A x on the device; x, y global-length host vectors (owned entries of y written) */
 int nsb_spmv(nsb_handle h, const double* x_global, double* y_global);
+/* diagnostic: y_u = Dinv F x_u, the node-block-Jacobi scaled velocity block exactly as the velocity polynomial of the
+ * preconditioner applies it (operator and precision per nsb_solver_opts); only velocity entries are read / written */
+int nsb_apply_velocity_block(nsb_handle h, const double* x_global, double* y_global);
 
 /* ---- measurement ------------------------------------------------------------------ */
 /* CUDA-event timing on the library's stream */

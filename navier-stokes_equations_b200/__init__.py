@@ -31,7 +31,8 @@ class NsbParams(C.Structure):
 
 class NsbSolverOpts(C.Structure):
     _fields_ = [("poly_degree_F", C.c_int32), ("poly_refresh", C.c_int32), ("poly_kind", C.c_int32), ("poly_target", C.c_double), ("cheb_degree_Mp", C.c_int32),
-                ("amg_smoother_degree", C.c_int32), ("schur_mass_coeff", C.c_double), ("reorthogonalize", C.c_int32), ("precond_precision", C.c_int32)]
+                ("amg_smoother_degree", C.c_int32), ("schur_mass_coeff", C.c_double), ("reorthogonalize", C.c_int32), ("precond_precision", C.c_int32),
+                ("precond_operator", C.c_int32)]
 
 
 _lib = None
@@ -141,9 +142,15 @@ class Device:
         self._ck(lib().nsb_set_params(self.h, C.byref(p)))
 
     def set_solver_opts(self, poly_degree_F=0, poly_refresh=0, poly_kind=0, poly_target=0.0, cheb_degree_Mp=0, amg_smoother_degree=0,
-                        schur_mass_coeff=0.0, reorthogonalize=1, precond_precision=0):
-        o = NsbSolverOpts(poly_degree_F, poly_refresh, poly_kind, poly_target, cheb_degree_Mp, amg_smoother_degree, schur_mass_coeff, reorthogonalize, precond_precision)
+                        schur_mass_coeff=0.0, reorthogonalize=1, precond_precision=0, precond_operator=0):
+        o = NsbSolverOpts(poly_degree_F, poly_refresh, poly_kind, poly_target, cheb_degree_Mp, amg_smoother_degree, schur_mass_coeff, reorthogonalize, precond_precision,
+                          precond_operator)
         self._ck(lib().nsb_set_solver_opts(self.h, C.byref(o)))
+
+    def get_solver_opts(self):
+        o = NsbSolverOpts()
+        self._ck(lib().nsb_get_solver_opts(self.h, C.byref(o)))
+        return {k: getattr(o, k) for k, _ in NsbSolverOpts._fields_}
 
     def set_vector(self, which, v):
         v = np.ascontiguousarray(v, np.float64)
@@ -201,6 +208,13 @@ class Device:
         x = np.ascontiguousarray(x, np.float64)
         y = np.zeros(self.n_dofs)
         self._ck(lib().nsb_spmv(self.h, _p(x, C.c_double), _p(y, C.c_double)))
+        return y
+
+    def apply_velocity_block(self, x):
+        """y_u = Dinv F x_u with the operator the velocity polynomial uses (diagnostic)."""
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.zeros(self.n_dofs)
+        self._ck(lib().nsb_apply_velocity_block(self.h, _p(x, C.c_double), _p(y, C.c_double)))
         return y
 
     # ---- measurement

@@ -288,6 +288,7 @@ struct RowOut {
   double* rhs;             // [n_own]
   double* dinv;            // [nn_own][DIM*DIM]  inverse of the node-diagonal velocity block (preconditioner)
   float* vals_f;           // optional fp32 copy of F, node-interleaved (see k_spmv_vel_f32), may be null
+  float* s_rows;           // optional: S_e[a][b] per (node, cell) pair, blocked by 32 pairs (see ebe.cuh), may be null
 };
 
 template <int DIM, bool NEWTON>
@@ -459,6 +460,10 @@ k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double
 #pragma unroll
       for (int k = 0; k < DIM; ++k) trG += shfl_d(Gdd, grp + k);
       const double Sab = absJ * T.Mhat[a][b] * P.inv_dt + P.theta * P.nu * trG + Svar;
+      if (!NEWTON && out.s_rows && act && d == 0) {
+        const long long p = kc0 + ic;
+        out.s_rows[(size_t)(p >> 5) * (NN * 32) + b * 32 + (int)(p & 31)] = (float)Sab;
+      }
       double val[DIM];
 #pragma unroll
       for (int c = 0; c < DIM; ++c) val[c] = P.gamma * G[c] + ((c == d) ? Sab : 0.0);

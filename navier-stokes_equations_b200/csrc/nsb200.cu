@@ -20,6 +20,7 @@
 #include "assemble.cuh"
 #include "device.cuh"
 #include "linalg.cuh"
+#include "ebe.cuh"
 #include "structure.hpp"
 
 using namespace nsb;
@@ -211,6 +212,12 @@ struct nsb_ctx {
   nsb_solver_opts opt{};
   DBuf<double> vals, dinv, ctx, cell_rhs;
   DBuf<float> vals_f;               // fp32 copy of the values: operator of the velocity polynomial
+  // element-wise velocity operator (ebe.cuh): per-pair rows of S_e and tile-local node positions
+  DBuf<float> s_rows;
+  DBuf<unsigned short> d_pair_loc;
+  int ebe_smem_bytes = 0;
+  bool ebe_valid = false;           // s_rows describe the currently assembled (linearised) system
+  double ebe_gamma = 0.0;
   int ctx_stride = 0;
   // pressure matrices (global, replicated)
   HostCsr h_Mp, h_Kp;
@@ -257,6 +264,17 @@ int fail(nsb_ctx* c, const std::string& m, int code = -1) {
   catch (const std::exception& e) { return fail(c, e.what()); }
 
 inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+
+// operator used inside the velocity polynomial: 1 = assembled copy (fp32 / fp64), 2 = element-wise (ebe.cuh)
+#ifndef NSB_DEFAULT_PRECOND_OPERATOR
+#define NSB_DEFAULT_PRECOND_OPERATOR 1
+#endif
+
+// the node-interleaved fp32 copy of F is only kept when the assembled operator runs in fp32
+size_t vals_f_size(const nsb_ctx* c) {
+  if (c->opt.precond_precision == 64 || c->opt.precond_operator == 2) return 0;
+  return (size_t)c->S.nbr.size() * c->dim * (c->dim == 3 ? 4 : 2);
+}
 
 // ---- halo exchange of one local vector (ghost tail refreshed from the owners) -----------
 void halo_exchange(nsb_ctx* c, double* v) {
@@ -323,7 +341,9 @@ template <int DIM> void launch_assemble(nsb_ctx* c, bool newton) {
     k_cell_context<DIM, false><<<cgrid, ASM_WARPS * 32, 0, c->stream>>>(c->M, P, c->d_fe.p, vecA, vecB, c->ctx.p, c->cell_rhs.p);
   c->launch_check();
   c->prof.end(id, c->stream);
-  RowOut out{c->vals.p, c->v_rhs.p, c->dinv.p, c->vals_f.p};
+  RowOut out{c->vals.p, c->v_rhs.p, c->dinv.p, c->vals_f.p, newton ? nullptr : c->s_rows.p};
+  c->ebe_valid = !newton && c->s_rows.p != nullptr;
+  c->ebe_gamma = P.gamma;
   id = c->prof.begin(PC_ASM_ROWS, c->stream);
   if (newton)
     k_node_rows<DIM, true><<<c->n_tiles, ASM_WARPS * 32, c->tile_smem_bytes, c->stream>>>(c->M, P, c->ctx.p, c->cell_rhs.p, c->cflag.p, c->cval.p, out, c->d_tile_ptr.p, c->d_fe.p);
@@ -336,6 +356,11 @@ template <int DIM> void launch_assemble(nsb_ctx* c, bool newton) {
 template <int DIM> void set_smem_attr(int bytes) {
   CK(cudaFuncSetAttribute(k_node_rows<DIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute(k_node_rows<DIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+}
+
+template <int DIM> void set_ebe_attr(int bytes) {
+  CK(cudaFuncSetAttribute(k_apply_F_ebe<DIM, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CK(cudaFuncSetAttribute(k_apply_F_ebe<DIM, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 }
 
 // y(owned) = A x ; x must have a valid ghost tail
@@ -351,7 +376,11 @@ template <int MODE>
 void spmv_vel(nsb_ctx* c, const double* x, double* y, const double* u, double* poly, PolyCoef pc) {
   size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
   const int g = c->n_stiles;
-  if (c->vals_f.p && MODE != 0) {
+  if (c->ebe_valid && MODE != 0) {
+    const EbeData E{c->s_rows.p, c->d_pair_loc.p, c->cflag.p, c->ebe_gamma};
+    if (c->dim == 2) k_apply_F_ebe<2, MODE><<<g, EBE_THREADS, c->ebe_smem_bytes, c->stream>>>(c->M, c->stiles, E, c->d_fe.p, x, y, u, poly, c->dinv.p, pc);
+    else k_apply_F_ebe<3, MODE><<<g, EBE_THREADS, c->ebe_smem_bytes, c->stream>>>(c->M, c->stiles, E, c->d_fe.p, x, y, u, poly, c->dinv.p, pc);
+  } else if (c->vals_f.p && MODE != 0) {
     if (c->dim == 2) k_spmv_vel_f32<2, MODE><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float2*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
     else k_spmv_vel_f32<3, MODE><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float4*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
   } else {
@@ -864,6 +893,36 @@ void build_tiles(nsb_ctx* c) {
       ++tile;
     }
     c->n_stiles = (int)sp.size() - 1;
+    // element-wise velocity operator: tile-local position of every cell node of every (node, cell) pair,
+    // blocked by 32 pairs like the S rows the assembly writes (ebe.cuh); shared memory for the pair results
+    {
+      const int NN = S.NN;
+      const int64_t NP = (int64_t)S.n2c.size();
+      int max_pairs = 0;
+      for (size_t t = 0; t + 1 < sp.size(); ++t)
+        max_pairs = std::max(max_pairs, (int)(S.n2c_ptr[sp[t + 1]] - S.n2c_ptr[sp[t]]));
+      c->ebe_smem_bytes = max_pairs * S.dim * (int)sizeof(double);
+      if (c->opt.precond_operator == 2) {
+        std::vector<unsigned short> pl((size_t)((NP + 31) / 32) * 32 * NN, 0);
+#pragma omp parallel for schedule(static)
+        for (int B = 0; B < S.nn_own; ++B)
+          for (int64_t k = S.n2c_ptr[B]; k < S.n2c_ptr[B + 1]; ++k) {
+            const uint32_t pk = S.n2c[k];
+            const size_t cell = pk >> 4, a = pk & 15u;
+            for (int b = 0; b < NN; ++b) {
+              const int rk = S.rank_uu[(cell * NN + a) * NN + b];
+              pl[(size_t)(k >> 5) * (NN * 32) + (size_t)b * 32 + (size_t)(k & 31)] = nloc[S.nbr_ptr[B] + rk];
+            }
+          }
+        c->d_pair_loc.upload(pl, c->stream);
+        c->s_rows.alloc(pl.size());
+        CK(cudaMemsetAsync(c->s_rows.p, 0, pl.size() * sizeof(float), c->stream));
+      } else {
+        c->d_pair_loc.alloc(0);
+        c->s_rows.alloc(0);
+      }
+      c->ebe_valid = false;
+    }
     c->d_stile_ptr.upload(sp, c->stream);
     c->d_suniq_ptr.upload(uptr, c->stream); c->d_suniq_xoff.upload(uxoff, c->stream);
     c->d_spuniq_ptr.upload(pptr, c->stream); c->d_spuniq_xoff.upload(pxoff, c->stream);
@@ -877,6 +936,9 @@ void build_tiles(nsb_ctx* c) {
   CK(cudaStreamSynchronize(c->stream));
   if (c->dim == 2) set_smem_attr<2>(c->tile_smem_bytes);
   else set_smem_attr<3>(c->tile_smem_bytes);
+  if (c->ebe_smem_bytes + 28 * 1024 > dev_max) throw CudaErr{"the pair results of one SpMV tile do not fit in shared memory"};
+  if (c->dim == 2) set_ebe_attr<2>(c->ebe_smem_bytes);
+  else set_ebe_attr<3>(c->ebe_smem_bytes);
 }
 
 // one-time M_p, K_p on the host over the GLOBAL P1 graph (reference cpp:798-803, 812-829)
@@ -1003,6 +1065,7 @@ int nsb_create(int dim, int device, nsb_handle* out) {
   CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   c->opt.poly_degree_F = 64; c->opt.poly_refresh = 1; c->opt.poly_target = 0.08; c->opt.poly_kind = 1; c->opt.cheb_degree_Mp = 3;
   c->opt.amg_smoother_degree = 2; c->opt.schur_mass_coeff = -1.0; c->opt.reorthogonalize = 1; c->opt.precond_precision = 32;
+  c->opt.precond_operator = NSB_DEFAULT_PRECOND_OPERATOR;
   c->par.dt = 0.01; c->par.theta = 1.0; c->par.nu = 1e-3; c->par.rho = 1.0; c->par.gamma = 0.1;
   c->d_nrm.alloc(4);
   return 0;
@@ -1151,7 +1214,7 @@ int nsb_upload_mesh(nsb_handle c, int64_t n_vertices, const double* coords, int6
   CK(cudaMallocHost(&c->pin, nt * sizeof(double)));
   c->cflag.alloc(nt); c->cflag.zero(st);
   c->vals.alloc((size_t)S.nnz_local);
-  c->vals_f.alloc(c->opt.precond_precision == 64 ? 0 : (size_t)S.nbr.size() * dim * (dim == 3 ? 4 : 2));
+  c->vals_f.alloc(vals_f_size(c));
   c->dinv.alloc((size_t)S.nn_own * dim * dim);
   c->cell_rhs.alloc((size_t)S.nc * S.DPC);
   c->ctx_stride = 0;
@@ -1259,16 +1322,19 @@ int nsb_set_solver_opts(nsb_handle c, const nsb_solver_opts* o) {
   if (n.amg_smoother_degree <= 0) n.amg_smoother_degree = 2;
   if (n.schur_mass_coeff == 0.0) n.schur_mass_coeff = -1.0;
   if (n.precond_precision != 64) n.precond_precision = 32;
-  if (c->have_mesh && n.precond_precision != c->opt.precond_precision) {
-    // (de)allocate the fp32 operator copy; it is refilled by the next assembly
+  if (n.precond_operator != 1 && n.precond_operator != 2) n.precond_operator = NSB_DEFAULT_PRECOND_OPERATOR;
+  const bool changed = n.precond_precision != c->opt.precond_precision || n.precond_operator != c->opt.precond_operator;
+  c->opt = n;
+  if (c->have_mesh && changed) {
+    // (de)allocate the operator copies of the velocity polynomial; they are refilled by the next assembly
     try {
       cudaSetDevice(c->device);
-      c->vals_f.alloc(n.precond_precision == 64 ? 0 : (size_t)c->S.nbr.size() * c->dim * (c->dim == 3 ? 4 : 2));
+      c->vals_f.alloc(vals_f_size(c));
+      build_tiles(c);
     } catch (const CudaErr& e) { return fail(c, e.msg); }
     c->have_matrix = false;
     c->poly_roots.clear();
   }
-  c->opt = n;
   return 0;
 }
 
@@ -1501,6 +1567,26 @@ int nsb_spmv(nsb_handle c, const double* xg, double* yg) {
   NSB_CATCH(c)
 }
 
+int nsb_apply_velocity_block(nsb_handle c, const double* xg, double* yg) {
+  if (!c || !c->have_matrix) return fail(c, "no assembled system");
+  NSB_TRY
+  CK(cudaSetDevice(c->device));
+  const Structure& S = c->S;
+  std::vector<double> loc(S.n_tot_dofs(), 0.0);
+  const int dim = c->dim;
+  for (int A = 0; A < S.nn_own + S.nn_ghost; ++A)
+    for (int k = 0; k < dim; ++k) loc[S.node_xoff(A) + k] = xg[S.node_gid[A] * dim + k];
+  CK(cudaMemcpyAsync(c->w_pin.p, loc.data(), loc.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  spmv_vel<2>(c, c->w_pin.p, c->w_tmp.p, nullptr, nullptr, PolyCoef{});
+  std::vector<double> out((size_t)dim * S.nn_own);
+  CK(cudaMemcpyAsync(out.data(), c->w_tmp.p, out.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int A = 0; A < S.nn_own; ++A)
+    for (int k = 0; k < dim; ++k) yg[S.node_gid[A] * dim + k] = out[(size_t)dim * A + k];
+  return 0;
+  NSB_CATCH(c)
+}
+
 int nsb_timer_start(nsb_handle c) {
   if (!c) return -1;
   cudaSetDevice(c->device);
@@ -1634,6 +1720,12 @@ int nsb_solver_info(nsb_handle c, int* poly_degree, double* poly_probe_residual,
   }
   if (poly_probe_residual) *poly_probe_residual = c->poly_probe_res;
   if (amg_levels) *amg_levels = (int)c->amg.size();
+  return 0;
+}
+
+int nsb_get_solver_opts(nsb_handle c, nsb_solver_opts* o) {
+  if (!c || !o) return -1;
+  *o = c->opt;
   return 0;
 }
 
