@@ -27,17 +27,23 @@ constexpr int EBE_THREADS = 256;
 struct EbeData {
   const float* s_rows;               // [ceil(NP/32)][NN][32]  S_e[a][b] of pair p at (p>>5, b, p&31)
   const unsigned short* pair_loc;    // same blocking: position of cell node b in the tile's unique list
+  const unsigned short* pair_ca;     // [NP] (position of the pair's cell in the tile's unique cell list) << 4 | local node a
+  const int* tile_cell_ptr;          // [n_tiles+1] into tile_cells
+  const int* tile_cells;             // unique local cells touched by the tile's pairs
   const unsigned char* cflag;        // Dirichlet flag per local DoF
   double gamma;                      // grad-div weight (0 without SUPG)
+  int ypair_doubles;                 // size of the pair-result region of the dynamic shared memory
 };
 
 template <int DIM, int MODE>
-__global__ void __launch_bounds__(EBE_THREADS)
+__global__ void __launch_bounds__(EBE_THREADS, 3)
 k_apply_F_ebe(DevMesh M, SpmvTiles TL, EbeData E, const FeTables* __restrict__ gT, const double* __restrict__ x,
               double* __restrict__ y, const double* __restrict__ u, double* __restrict__ poly,
               const double* __restrict__ dinv, PolyCoef pc) {
   constexpr int NV = DIM + 1, NN = Fe<DIM>::NN;
-  extern __shared__ double ypair[];                 // [pairs of the tile][DIM]
+  constexpr int GEO_N = NV * DIM + 1;               // grad lambda [NV][DIM], |J|   (odd: spreads the banks)
+  extern __shared__ double ypair[];                 // [pairs of the tile][DIM], then the geometry of the tile's cells
+  double* geo_s = ypair + E.ypair_doubles;
   __shared__ double xs[TILE_MAX_UNIQ * DIM];
   __shared__ double KT[NN][2][2][NN];               // Khat transposed: row node a fastest (bank-conflict free)
   __shared__ double ysum[TILE_MAX_NODES * DIM];
@@ -54,6 +60,13 @@ k_apply_F_ebe(DevMesh M, SpmvTiles TL, EbeData E, const FeTables* __restrict__ g
     KT[b][sa][sb][a] = gT->Khat[a][b][sa][sb];
   }
   if (tid < NN * 2) s_ia[tid / 2][tid % 2] = gT->idx[tid / 2][tid % 2];
+  // geometry of the tile's unique cells: per-thread loads of the 128-byte cell records would be 32 sectors per
+  // request (the L1 tag stage becomes the limit), so they are staged once per tile with coalesced loads
+  const int c0 = E.tile_cell_ptr[t], nuc = E.tile_cell_ptr[t + 1] - c0;
+  for (int i = tid; i < nuc * GEO_N; i += EBE_THREADS) {
+    const int k = i % GEO_N;
+    geo_s[i] = __ldg(M.cell_geom + (size_t)__ldg(E.tile_cells + c0 + i / GEO_N) * 16 + (k < NV * DIM ? k : 12));
+  }
   const long long p0 = M.n2c_ptr[n0];
   const int npairs = (int)(M.n2c_ptr[n1] - p0);
   __syncthreads();
@@ -61,8 +74,8 @@ k_apply_F_ebe(DevMesh M, SpmvTiles TL, EbeData E, const FeTables* __restrict__ g
   // ---- phase 1: one thread per (node, cell) pair
   for (int i = tid; i < npairs; i += EBE_THREADS) {
     const long long p = p0 + i;
-    const uint32_t pk = __ldg(M.n2c + p);
-    const int cell = (int)(pk >> 4), a = (int)(pk & 15u);
+    const unsigned ca = __ldg(E.pair_ca + p);
+    const int a = (int)(ca & 15u);
     const size_t base = (size_t)(p >> 5) * (NN * 32) + (size_t)(p & 31);
     float Sv[NN];
     unsigned short lc[NN];
@@ -71,13 +84,13 @@ k_apply_F_ebe(DevMesh M, SpmvTiles TL, EbeData E, const FeTables* __restrict__ g
       Sv[b] = __ldcs(E.s_rows + base + b * 32);
       lc[b] = __ldcs(E.pair_loc + base + b * 32);
     }
-    const double* geo = M.cell_geom + (size_t)cell * 16;
+    const double* geo = geo_s + (int)(ca >> 4) * GEO_N;
     double g[NV][DIM];
 #pragma unroll
     for (int v = 0; v < NV; ++v)
 #pragma unroll
-      for (int k = 0; k < DIM; ++k) g[v][k] = __ldg(geo + v * DIM + k);
-    const double ga = E.gamma * __ldg(geo + 12);
+      for (int k = 0; k < DIM; ++k) g[v][k] = geo[v * DIM + k];
+    const double ga = E.gamma * geo[NV * DIM];
     double yv[DIM];
 #pragma unroll
     for (int c = 0; c < DIM; ++c) yv[c] = 0.0;
@@ -109,7 +122,7 @@ k_apply_F_ebe(DevMesh M, SpmvTiles TL, EbeData E, const FeTables* __restrict__ g
     w0 *= ga; w1 *= ga;
 #pragma unroll
     for (int c = 0; c < DIM; ++c) {
-      yv[c] += __ldg(geo + ia0 * DIM + c) * w0 + __ldg(geo + ia1 * DIM + c) * w1;
+      yv[c] += geo[ia0 * DIM + c] * w0 + geo[ia1 * DIM + c] * w1;
       ypair[i * DIM + c] = yv[c];
     }
   }

@@ -214,8 +214,9 @@ struct nsb_ctx {
   DBuf<float> vals_f;               // fp32 copy of the values: operator of the velocity polynomial
   // element-wise velocity operator (ebe.cuh): per-pair rows of S_e and tile-local node positions
   DBuf<float> s_rows;
-  DBuf<unsigned short> d_pair_loc;
-  int ebe_smem_bytes = 0;
+  DBuf<unsigned short> d_pair_loc, d_pair_ca;
+  DBuf<int> d_tile_cell_ptr, d_tile_cells;
+  int ebe_smem_bytes = 0, ebe_ypair_doubles = 0;
   bool ebe_valid = false;           // s_rows describe the currently assembled (linearised) system
   double ebe_gamma = 0.0;
   int ctx_stride = 0;
@@ -377,7 +378,8 @@ void spmv_vel(nsb_ctx* c, const double* x, double* y, const double* u, double* p
   size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
   const int g = c->n_stiles;
   if (c->ebe_valid && MODE != 0) {
-    const EbeData E{c->s_rows.p, c->d_pair_loc.p, c->cflag.p, c->ebe_gamma};
+    const EbeData E{c->s_rows.p, c->d_pair_loc.p, c->d_pair_ca.p, c->d_tile_cell_ptr.p, c->d_tile_cells.p, c->cflag.p, c->ebe_gamma,
+                    c->ebe_ypair_doubles};
     if (c->dim == 2) k_apply_F_ebe<2, MODE><<<g, EBE_THREADS, c->ebe_smem_bytes, c->stream>>>(c->M, c->stiles, E, c->d_fe.p, x, y, u, poly, c->dinv.p, pc);
     else k_apply_F_ebe<3, MODE><<<g, EBE_THREADS, c->ebe_smem_bytes, c->stream>>>(c->M, c->stiles, E, c->d_fe.p, x, y, u, poly, c->dinv.p, pc);
   } else if (c->vals_f.p && MODE != 0) {
@@ -901,9 +903,10 @@ void build_tiles(nsb_ctx* c) {
       int max_pairs = 0;
       for (size_t t = 0; t + 1 < sp.size(); ++t)
         max_pairs = std::max(max_pairs, (int)(S.n2c_ptr[sp[t + 1]] - S.n2c_ptr[sp[t]]));
-      c->ebe_smem_bytes = max_pairs * S.dim * (int)sizeof(double);
+      c->ebe_ypair_doubles = max_pairs * S.dim;
+      c->ebe_smem_bytes = 0;
       if (c->opt.precond_operator == 2) {
-        std::vector<unsigned short> pl((size_t)((NP + 31) / 32) * 32 * NN, 0);
+        std::vector<unsigned short> pl((size_t)((NP + 31) / 32) * 32 * NN, 0), pca((size_t)NP, 0);
 #pragma omp parallel for schedule(static)
         for (int B = 0; B < S.nn_own; ++B)
           for (int64_t k = S.n2c_ptr[B]; k < S.n2c_ptr[B + 1]; ++k) {
@@ -914,11 +917,32 @@ void build_tiles(nsb_ctx* c) {
               pl[(size_t)(k >> 5) * (NN * 32) + (size_t)b * 32 + (size_t)(k & 31)] = nloc[S.nbr_ptr[B] + rk];
             }
           }
+        // unique cells per tile (ascending) and the pair's position in that list
+        std::vector<int> tcp(1, 0), tcells, cpos(S.nc, 0), uc;
+        int max_ucells = 0;
+        for (size_t t = 0; t + 1 < sp.size(); ++t) {
+          uc.clear();
+          for (int64_t k = S.n2c_ptr[sp[t]]; k < S.n2c_ptr[sp[t + 1]]; ++k) uc.push_back((int)(S.n2c[k] >> 4));
+          std::sort(uc.begin(), uc.end());
+          uc.erase(std::unique(uc.begin(), uc.end()), uc.end());
+          if (uc.size() > 4096) throw CudaErr{"an SpMV tile touches more than 4096 cells"};
+          for (size_t i = 0; i < uc.size(); ++i) cpos[uc[i]] = (int)i;
+          for (int64_t k = S.n2c_ptr[sp[t]]; k < S.n2c_ptr[sp[t + 1]]; ++k)
+            pca[k] = (unsigned short)((cpos[S.n2c[k] >> 4] << 4) | (S.n2c[k] & 15u));
+          tcells.insert(tcells.end(), uc.begin(), uc.end());
+          tcp.push_back((int)tcells.size());
+          max_ucells = std::max(max_ucells, (int)uc.size());
+        }
+        c->ebe_smem_bytes = (c->ebe_ypair_doubles + max_ucells * ((S.dim + 1) * S.dim + 1)) * (int)sizeof(double);
         c->d_pair_loc.upload(pl, c->stream);
+        c->d_pair_ca.upload(pca, c->stream);
+        c->d_tile_cell_ptr.upload(tcp, c->stream);
+        c->d_tile_cells.upload(tcells, c->stream);
         c->s_rows.alloc(pl.size());
         CK(cudaMemsetAsync(c->s_rows.p, 0, pl.size() * sizeof(float), c->stream));
       } else {
-        c->d_pair_loc.alloc(0);
+        c->d_pair_loc.alloc(0); c->d_pair_ca.alloc(0);
+        c->d_tile_cell_ptr.alloc(0); c->d_tile_cells.alloc(0);
         c->s_rows.alloc(0);
       }
       c->ebe_valid = false;

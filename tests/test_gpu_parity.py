@@ -294,10 +294,10 @@ def test_solver_options_reach_the_same_solution(case3d):
         x = c.dev.get_vector(nsb.NSB_SOLUTION)
         assert ok, opts
         assert np.linalg.norm(x - x0) / np.linalg.norm(x0) < 1e-9, opts
-    c.dev.set_solver_opts()
-    c.dev.assemble_linearized()
     info = c.dev.solver_info()
     assert info["amg_levels"] >= 1 and info["poly_degree"] >= 1
+    c.dev.set_solver_opts()
+    c.dev.assemble_linearized()
 
 
 def test_newton_iterations_3d_supg_match_oracle(case3d):
