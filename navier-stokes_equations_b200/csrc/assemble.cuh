@@ -288,7 +288,7 @@ struct RowOut {
   double* rhs;             // [n_own]
   double* dinv;            // [nn_own][DIM*DIM]  inverse of the node-diagonal velocity block (preconditioner)
   float* vals_f;           // optional fp32 copy of F, node-interleaved (see k_spmv_vel_f32), may be null
-  float* s_rows;           // optional: S_e[a][b] per (node, cell) pair, blocked by 32 pairs (see ebe.cuh), may be null
+  float* s_rows;           // optional: S_e[a][b] per (node, cell) pair at ebe_index(pair, b) (see ebe.cuh), may be null
 };
 
 template <int DIM, bool NEWTON>
@@ -462,7 +462,7 @@ k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double
       const double Sab = absJ * T.Mhat[a][b] * P.inv_dt + P.theta * P.nu * trG + Svar;
       if (!NEWTON && out.s_rows && act && d == 0) {
         const long long p = kc0 + ic;
-        out.s_rows[(size_t)(p >> 5) * (NN * 32) + b * 32 + (int)(p & 31)] = (float)Sab;
+        out.s_rows[((size_t)(p >> 5) * (NN / 2) + (size_t)(b >> 1)) * 64 + (size_t)(p & 31) * 2 + (size_t)(b & 1)] = (float)Sab;
       }
       double val[DIM];
 #pragma unroll

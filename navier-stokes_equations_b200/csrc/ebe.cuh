@@ -25,7 +25,7 @@ namespace nsb {
 constexpr int EBE_THREADS = 256;
 
 struct EbeData {
-  const float* s_rows;               // [ceil(NP/32)][NN][32]  S_e[a][b] of pair p at (p>>5, b, p&31)
+  const float* s_rows;               // S_e[a][b] of pair p at ebe_index(p, b)  (blocked by 32 pairs, see below)
   const unsigned short* pair_loc;    // same blocking: position of cell node b in the tile's unique list
   const unsigned short* pair_ca;     // [NP] (position of the pair's cell in the tile's unique cell list) << 4 | local node a
   const int* tile_cell_ptr;          // [n_tiles+1] into tile_cells
@@ -35,21 +35,67 @@ struct EbeData {
   int ypair_doubles;                 // size of the pair-result region of the dynamic shared memory
 };
 
+// index of (pair p, cell node b) in the blocked pair arrays: 32 pairs x 2 consecutive b per 256-byte (floats) /
+// 128-byte (positions) warp row, so a lane fetches two b with one 8- / 4-byte load
+template <int NN> __host__ __device__ inline size_t ebe_index(long long p, int b) {
+  return ((size_t)(p >> 5) * (NN / 2) + (size_t)(b >> 1)) * 64 + (size_t)(p & 31) * 2 + (size_t)(b & 1);
+}
+
 template <int DIM, int MODE>
 __global__ void __launch_bounds__(EBE_THREADS, 3)
 k_apply_F_ebe(DevMesh M, SpmvTiles TL, EbeData E, const FeTables* __restrict__ gT, const double* __restrict__ x,
               double* __restrict__ y, const double* __restrict__ u, double* __restrict__ poly,
               const double* __restrict__ dinv, PolyCoef pc) {
-  constexpr int NV = DIM + 1, NN = Fe<DIM>::NN;
+  constexpr int NV = DIM + 1, NN = Fe<DIM>::NN, NH = NN / 2;
   constexpr int GEO_N = NV * DIM + 1;               // grad lambda [NV][DIM], |J|   (odd: spreads the banks)
+  static_assert(NN % 2 == 0, "pair arrays hold two cell nodes per element");
+  static_assert(TILE_MAX_NODES * 4 <= EBE_THREADS, "one thread per (node, component slot) in the row phase");
   extern __shared__ double ypair[];                 // [pairs of the tile][DIM], then the geometry of the tile's cells
   double* geo_s = ypair + E.ypair_doubles;
   __shared__ double xs[TILE_MAX_UNIQ * DIM];
   __shared__ double KT[NN][2][2][NN];               // Khat transposed: row node a fastest (bank-conflict free)
-  __shared__ double ysum[TILE_MAX_NODES * DIM];
   __shared__ int s_ia[NN][2];
   const int t = blockIdx.x, tid = threadIdx.x;
   const int n0 = TL.node_ptr[t], n1 = TL.node_ptr[t + 1], nn = n1 - n0;
+  const long long p0 = M.n2c_ptr[n0];
+  const int npairs = (int)(M.n2c_ptr[n1] - p0);
+
+  // ---- every load that does not depend on staged data is issued first, so that its latency overlaps the staging
+  // (a) operands of the row phase: thread (s, c) = (tid / 4, tid % 4) owns row (n0 + s, c)
+  const int rs = tid >> 2, rc = tid & 3;
+  const bool has_row = rs < nn && rc < DIM;
+  int q0 = 0, q1 = 0;
+  double dv[DIM], uv = 0.0, pv = 0.0, xown = 0.0;
+  bool crow = false;
+#pragma unroll
+  for (int e = 0; e < DIM; ++e) dv[e] = 0.0;
+  if (has_row) {
+    const int row = DIM * (n0 + rs) + rc;
+    q0 = (int)(M.n2c_ptr[n0 + rs] - p0);
+    q1 = (int)(M.n2c_ptr[n0 + rs + 1] - p0);
+#pragma unroll
+    for (int e = 0; e < DIM; ++e) dv[e] = __ldg(dinv + (size_t)(n0 + rs) * DIM * DIM + rc * DIM + e);
+    crow = E.cflag[row] != 0;
+    xown = x[row];
+    if (MODE == 3) { uv = u[row]; pv = poly[row]; }
+  }
+  // (b) the first round of pair data
+  float2 Sv[NH];
+  unsigned lc[NH];
+  unsigned ca = 0;
+  auto load_pair = [&](int i) {
+    const long long p = p0 + i;
+    const size_t base = ebe_index<NN>(p, 0);
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      Sv[h] = __ldcs(reinterpret_cast<const float2*>(E.s_rows + base + (size_t)h * 64));
+      lc[h] = __ldcs(reinterpret_cast<const unsigned*>(E.pair_loc + base + (size_t)h * 64));
+    }
+    ca = __ldg(E.pair_ca + p);
+  };
+  if (tid < npairs) load_pair(tid);
+
+  // ---- staging: x of the unique neighbour nodes (Dirichlet columns zeroed), Khat, the cells' geometry
   const int u0 = TL.uniq_ptr[t], nuq = TL.uniq_ptr[t + 1] - u0;
   for (int i = tid; i < nuq * DIM; i += EBE_THREADS) {
     const int xo = __ldg(TL.uniq_xoff + u0 + i / DIM) + i % DIM;
@@ -60,30 +106,19 @@ k_apply_F_ebe(DevMesh M, SpmvTiles TL, EbeData E, const FeTables* __restrict__ g
     KT[b][sa][sb][a] = gT->Khat[a][b][sa][sb];
   }
   if (tid < NN * 2) s_ia[tid / 2][tid % 2] = gT->idx[tid / 2][tid % 2];
-  // geometry of the tile's unique cells: per-thread loads of the 128-byte cell records would be 32 sectors per
-  // request (the L1 tag stage becomes the limit), so they are staged once per tile with coalesced loads
+  // per-thread loads of the 128-byte cell records would be 32 sectors per request (the L1 tag stage becomes
+  // the limit), so the geometry of the tile's unique cells is staged once with coalesced loads
   const int c0 = E.tile_cell_ptr[t], nuc = E.tile_cell_ptr[t + 1] - c0;
   for (int i = tid; i < nuc * GEO_N; i += EBE_THREADS) {
     const int k = i % GEO_N;
     geo_s[i] = __ldg(M.cell_geom + (size_t)__ldg(E.tile_cells + c0 + i / GEO_N) * 16 + (k < NV * DIM ? k : 12));
   }
-  const long long p0 = M.n2c_ptr[n0];
-  const int npairs = (int)(M.n2c_ptr[n1] - p0);
   __syncthreads();
 
   // ---- phase 1: one thread per (node, cell) pair
   for (int i = tid; i < npairs; i += EBE_THREADS) {
-    const long long p = p0 + i;
-    const unsigned ca = __ldg(E.pair_ca + p);
+    if (i != tid) load_pair(i);
     const int a = (int)(ca & 15u);
-    const size_t base = (size_t)(p >> 5) * (NN * 32) + (size_t)(p & 31);
-    float Sv[NN];
-    unsigned short lc[NN];
-#pragma unroll
-    for (int b = 0; b < NN; ++b) {
-      Sv[b] = __ldcs(E.s_rows + base + b * 32);
-      lc[b] = __ldcs(E.pair_loc + base + b * 32);
-    }
     const double* geo = geo_s + (int)(ca >> 4) * GEO_N;
     double g[NV][DIM];
 #pragma unroll
@@ -97,11 +132,12 @@ k_apply_F_ebe(DevMesh M, SpmvTiles TL, EbeData E, const FeTables* __restrict__ g
     double w0 = 0.0, w1 = 0.0;
 #pragma unroll
     for (int b = 0; b < NN; ++b) {
-      const double* xb = xs + (int)lc[b] * DIM;
+      const int loc = (b & 1) ? (int)(lc[b >> 1] >> 16) : (int)(lc[b >> 1] & 0xffffu);
+      const double* xb = xs + loc * DIM;
       double xv[DIM];
 #pragma unroll
       for (int d = 0; d < DIM; ++d) xv[d] = xb[d];
-      const double s = (double)Sv[b];
+      const double s = (double)((b & 1) ? Sv[b >> 1].y : Sv[b >> 1].x);
 #pragma unroll
       for (int d = 0; d < DIM; ++d) yv[d] += s * xv[d];
       const int ib0 = node_i<DIM>(b), ib1 = node_j<DIM>(b);
@@ -128,35 +164,22 @@ k_apply_F_ebe(DevMesh M, SpmvTiles TL, EbeData E, const FeTables* __restrict__ g
   }
   __syncthreads();
 
-  // ---- phase 2: ordered sum over the pairs of each (node, component)
-  for (int r = tid; r < nn * DIM; r += EBE_THREADS) {
-    const int s = r / DIM, c = r % DIM;
-    const int q0 = (int)(M.n2c_ptr[n0 + s] - p0), q1 = (int)(M.n2c_ptr[n0 + s + 1] - p0);
-    double sum = 0.0;
-    for (int q = q0; q < q1; ++q) sum += ypair[q * DIM + c];
-    ysum[r] = sum;
-  }
-  __syncthreads();
-
-  // ---- phase 3: block-Jacobi scaling + polynomial step (same algebra as vel_epilogue)
-  for (int r = tid; r < nn * DIM; r += EBE_THREADS) {
-    const int s = r / DIM, c = r % DIM;
-    const int row = DIM * (n0 + s) + c;
-    double tt;
-    if (E.cflag[row]) {
-      tt = x[row];                                   // Dirichlet row: Dinv F acts as the identity
-    } else {
-      tt = 0.0;
+  // ---- phase 2: ordered sum over the pairs of each row, block-Jacobi scaling and the polynomial step (same
+  // algebra as vel_epilogue).  The DIM rows of a node sit in adjacent lanes of one 4-lane group.
+  double sum = 0.0;
+  for (int q = q0; q < q1; ++q) sum += ypair[q * DIM + (rc < DIM ? rc : 0)];
+  double tt = 0.0;
 #pragma unroll
-      for (int e = 0; e < DIM; ++e) tt += __ldg(dinv + (size_t)(n0 + s) * DIM * DIM + c * DIM + e) * ysum[s * DIM + e];
-    }
+  for (int e = 0; e < DIM; ++e) tt += dv[e] * __shfl_sync(NSB_FULL, sum, (tid & 28) + e);
+  if (has_row) {
+    const int row = DIM * (n0 + rs) + rc;
+    if (crow) tt = xown;                             // Dirichlet row: Dinv F acts as the identity
     if (MODE == 2) {
       y[row] = tt;
     } else {
-      const double uv = u[row];
       const double yn = pc.cu * uv + pc.ct * tt;
       y[row] = yn;
-      poly[row] = poly[row] + pc.cpu * uv + pc.cpy * yn;
+      poly[row] = pv + pc.cpu * uv + pc.cpy * yn;
     }
   }
 }

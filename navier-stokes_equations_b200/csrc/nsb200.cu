@@ -914,7 +914,7 @@ void build_tiles(nsb_ctx* c) {
             const size_t cell = pk >> 4, a = pk & 15u;
             for (int b = 0; b < NN; ++b) {
               const int rk = S.rank_uu[(cell * NN + a) * NN + b];
-              pl[(size_t)(k >> 5) * (NN * 32) + (size_t)b * 32 + (size_t)(k & 31)] = nloc[S.nbr_ptr[B] + rk];
+              pl[((size_t)(k >> 5) * (NN / 2) + (size_t)(b >> 1)) * 64 + (size_t)(k & 31) * 2 + (size_t)(b & 1)] = nloc[S.nbr_ptr[B] + rk];
             }
           }
         // unique cells per tile (ascending) and the pair's position in that list
