@@ -53,7 +53,6 @@ k_apply_F_ebe(DevMesh M, SpmvTiles TL, EbeData E, const FeTables* __restrict__ g
   extern __shared__ double ypair[];                 // [pairs of the tile][DIM], then the geometry of the tile's cells
   double* geo_s = ypair + E.ypair_doubles;
   __shared__ double xs[TILE_MAX_UNIQ * DIM];
-  __shared__ double KT[NN][2][2][NN];               // Khat transposed: row node a fastest (bank-conflict free)
   __shared__ int s_ia[NN][2];
   const int t = blockIdx.x, tid = threadIdx.x;
   const int n0 = TL.node_ptr[t], n1 = TL.node_ptr[t + 1], nn = n1 - n0;
@@ -101,10 +100,6 @@ k_apply_F_ebe(DevMesh M, SpmvTiles TL, EbeData E, const FeTables* __restrict__ g
     const int xo = __ldg(TL.uniq_xoff + u0 + i / DIM) + i % DIM;
     xs[i] = E.cflag[xo] ? 0.0 : __ldg(x + xo);
   }
-  for (int i = tid; i < NN * 4 * NN; i += EBE_THREADS) {
-    const int a = i % NN, sb = (i / NN) % 2, sa = (i / (2 * NN)) % 2, b = i / (4 * NN);
-    KT[b][sa][sb][a] = gT->Khat[a][b][sa][sb];
-  }
   if (tid < NN * 2) s_ia[tid / 2][tid % 2] = gT->idx[tid / 2][tid % 2];
   // per-thread loads of the 128-byte cell records would be 32 sectors per request (the L1 tag stage becomes
   // the limit), so the geometry of the tile's unique cells is staged once with coalesced loads
@@ -129,7 +124,13 @@ k_apply_F_ebe(DevMesh M, SpmvTiles TL, EbeData E, const FeTables* __restrict__ g
     double yv[DIM];
 #pragma unroll
     for (int c = 0; c < DIM; ++c) yv[c] = 0.0;
-    double w0 = 0.0, w1 = 0.0;
+    // grad-div part without the Khat table: div x_h is P1 on the cell, D(lambda) = sum_k Dk lambda_k with
+    //   Dk = 4 (z_k + sum over edges of the slot that differentiates w.r.t. lambda_k) - sum_vertices z_i,
+    // z_b^s = g_{i(b,s)} . x_b, and  int dN_a/dlambda D  follows from  int lambda_i lambda_k = m2 (1 + delta_ik),
+    // int lambda_k = m1  (products of linear functions: the quadrature rule of the assembly integrates them exactly)
+    double Dk[NV], Z = 0.0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) Dk[k] = 0.0;
 #pragma unroll
     for (int b = 0; b < NN; ++b) {
       const int loc = (b & 1) ? (int)(lc[b >> 1] >> 16) : (int)(lc[b >> 1] & 0xffffu);
@@ -144,18 +145,33 @@ k_apply_F_ebe(DevMesh M, SpmvTiles TL, EbeData E, const FeTables* __restrict__ g
       double z0 = 0.0;
 #pragma unroll
       for (int d = 0; d < DIM; ++d) z0 += g[ib0][d] * xv[d];
-      w0 += KT[b][0][0][a] * z0;
-      w1 += KT[b][1][0][a] * z0;
-      if (b >= NV) {
+      if (b < NV) {
+        Dk[ib0] += z0;                                 // d/dlambda_i of a vertex function: 4 lambda_i - 1
+        Z += z0;
+      } else {
         double z1 = 0.0;
 #pragma unroll
         for (int d = 0; d < DIM; ++d) z1 += g[ib1][d] * xv[d];
-        w0 += KT[b][0][1][a] * z1;
-        w1 += KT[b][1][1][a] * z1;
+        Dk[ib1] += z0;                                 // d/dlambda_i of 4 lambda_i lambda_j is 4 lambda_j
+        Dk[ib0] += z1;
       }
     }
+    constexpr double REFV = (DIM == 2) ? 0.5 : 1.0 / 6.0;
+    constexpr double m2 = REFV / ((DIM + 1) * (DIM + 2)), m1 = REFV / (DIM + 1);
+    double SD = 0.0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) { Dk[k] = 4.0 * Dk[k] - Z; SD += Dk[k]; }
     const int ia0 = s_ia[a][0], ia1 = s_ia[a][1];
-    w0 *= ga; w1 *= ga;
+    double Mi = 0.0, Mj = 0.0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const double Mk = m2 * (SD + Dk[k]);
+      if (k == ia0) Mi = Mk;
+      if (k == ia1) Mj = Mk;
+    }
+    const bool avert = a < NV;
+    const double w0 = ga * (avert ? 4.0 * Mi - m1 * SD : 4.0 * Mj);
+    const double w1 = avert ? 0.0 : ga * 4.0 * Mi;
 #pragma unroll
     for (int c = 0; c < DIM; ++c) {
       yv[c] += geo[ia0 * DIM + c] * w0 + geo[ia1 * DIM + c] * w1;
