@@ -22,7 +22,13 @@
 
 namespace nsb {
 
-constexpr int EBE_THREADS = 256;
+#ifndef NSB_EBE_THREADS
+#define NSB_EBE_THREADS 256
+#endif
+#ifndef NSB_EBE_MIN_CTAS
+#define NSB_EBE_MIN_CTAS 3
+#endif
+constexpr int EBE_THREADS = NSB_EBE_THREADS;
 
 struct EbeData {
   const float* s_rows;               // S_e[a][b] of pair p at ebe_index(p, b)  (blocked by 32 pairs, see below)
@@ -42,7 +48,7 @@ template <int NN> __host__ __device__ inline size_t ebe_index(long long p, int b
 }
 
 template <int DIM, int MODE>
-__global__ void __launch_bounds__(EBE_THREADS, 3)
+__global__ void __launch_bounds__(EBE_THREADS, NSB_EBE_MIN_CTAS)
 k_apply_F_ebe(DevMesh M, SpmvTiles TL, EbeData E, const FeTables* __restrict__ gT, const double* __restrict__ x,
               double* __restrict__ y, const double* __restrict__ u, double* __restrict__ poly,
               const double* __restrict__ dinv, PolyCoef pc) {

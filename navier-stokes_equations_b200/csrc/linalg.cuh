@@ -96,26 +96,26 @@ struct SpmvTiles {
   const unsigned short* pnbr_loc;        // parallel to pnbr_xoff
 };
 
-template <int DIM> struct TileSmem {
+template <int DIM, typename XT = double> struct TileSmem {
   int4 desc[TILE_MAX_NODES * 2];
-  double xs[TILE_MAX_UNIQ * DIM + TILE_MAX_PUNIQ];
+  XT xs[TILE_MAX_UNIQ * DIM + TILE_MAX_PUNIQ];
   unsigned short idx[TILE_MAX_IDX];
   int next, base_n, cnt_n, base_p, nuq;
 };
 
-template <int DIM, bool WITH_P>
+template <int DIM, bool WITH_P, typename XT = double>
 __device__ __forceinline__ void stage_tile(const DevMesh& M, const SpmvTiles& TL, int t, const double* __restrict__ x,
-                                           TileSmem<DIM>& T, int& n0, int& n1) {
+                                           TileSmem<DIM, XT>& T, int& n0, int& n1) {
   n0 = TL.node_ptr[t]; n1 = TL.node_ptr[t + 1];
   const int nn = n1 - n0;
   const int4* g = reinterpret_cast<const int4*>(M.nd + n0);
   for (int i = threadIdx.x; i < 2 * nn; i += blockDim.x) T.desc[i] = __ldg(g + i);
   // x values of the unique neighbours (independent of the descriptors)
   const int u0 = TL.uniq_ptr[t], nuq = TL.uniq_ptr[t + 1] - u0;
-  for (int i = threadIdx.x; i < nuq * DIM; i += blockDim.x) T.xs[i] = __ldg(x + __ldg(TL.uniq_xoff + u0 + i / DIM) + i % DIM);
+  for (int i = threadIdx.x; i < nuq * DIM; i += blockDim.x) T.xs[i] = (XT)__ldg(x + __ldg(TL.uniq_xoff + u0 + i / DIM) + i % DIM);
   if (WITH_P) {
     const int p0 = TL.puniq_ptr[t], npu = TL.puniq_ptr[t + 1] - p0;
-    for (int i = threadIdx.x; i < npu; i += blockDim.x) T.xs[nuq * DIM + i] = __ldg(x + __ldg(TL.puniq_xoff + p0 + i));
+    for (int i = threadIdx.x; i < npu; i += blockDim.x) T.xs[nuq * DIM + i] = (XT)__ldg(x + __ldg(TL.puniq_xoff + p0 + i));
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -137,8 +137,8 @@ __device__ __forceinline__ void stage_tile(const DevMesh& M, const SpmvTiles& TL
   __syncthreads();
 }
 
-template <int DIM>
-__device__ __forceinline__ NodeDesc desc_from_smem(const TileSmem<DIM>& T, int slot) {
+template <int DIM, typename XT>
+__device__ __forceinline__ NodeDesc desc_from_smem(const TileSmem<DIM, XT>& T, int slot) {
   const int4 a = T.desc[2 * slot], b = T.desc[2 * slot + 1];
   NodeDesc d;
   d.rowbase = ((long long)(unsigned)a.y << 32) | (unsigned)a.x;
@@ -330,6 +330,13 @@ template <> struct F32Vec<2> { using type = float2; };
 #ifndef NSB_F32_UNROLL
 #define NSB_F32_UNROLL 3
 #endif
+// storage of the staged x inside k_spmv_vel_f32: double keeps the operator exactly linear; float halves the
+// shared-memory gather traffic (experiment, see profiles/README.md)
+#ifdef NSB_XS32
+using F32X = float;
+#else
+using F32X = double;
+#endif
 constexpr int F32_UNROLL = NSB_F32_UNROLL;  // 3 x 32 columns covers the 81 columns of a line node in one trip
 
 template <int DIM, int MODE>
@@ -338,10 +345,10 @@ k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __rest
                const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ u,
                double* __restrict__ poly, const double* __restrict__ dinv, PolyCoef pc) {
   using V = typename F32Vec<DIM>::type;
-  __shared__ TileSmem<DIM> T;
+  __shared__ TileSmem<DIM, F32X> T;
   const int lane = threadIdx.x & 31;
   int n0, n1;
-  stage_tile<DIM, false>(M, TL, blockIdx.x, x, T, n0, n1);
+  stage_tile<DIM, false, F32X>(M, TL, blockIdx.x, x, T, n0, n1);
   for (;;) {
     int slot = 0;
     if (lane == 0) slot = atomicAdd(&T.next, 1);
@@ -357,6 +364,9 @@ k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __rest
     double sum[DIM];
 #pragma unroll
     for (int c = 0; c < DIM; ++c) sum[c] = 0.0;
+#ifdef NSB_F32_PLANAR
+    const float* pl = reinterpret_cast<const float*>(fv) + (long long)DIM * DIM * d.nbr0;
+#endif
     for (int k0 = 0; k0 < nbd; k0 += 32 * F32_UNROLL) {
       V v[F32_UNROLL];
       double xv[F32_UNROLL];
@@ -365,7 +375,16 @@ k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __rest
         const int k = k0 + 32 * q + lane;
         v[q] = V();
         xv[q] = 0.0;
-        if (k < nbd) { v[q] = NSB_STREAM_LOAD(rp + k); xv[q] = T.xs[(int)nx[k / DIM] * DIM + k % DIM]; }
+        if (k < nbd) {
+#ifdef NSB_F32_PLANAR
+          if (DIM == 3) {
+            v[q].x = NSB_STREAM_LOAD(pl + k); v[q].y = NSB_STREAM_LOAD(pl + nbd + k);
+            reinterpret_cast<float*>(&v[q])[DIM - 1] = NSB_STREAM_LOAD(pl + 2 * nbd + k);
+          } else
+#endif
+            v[q] = NSB_STREAM_LOAD(rp + k);
+          xv[q] = (double)T.xs[(int)nx[k / DIM] * DIM + k % DIM];
+        }
       }
 #pragma unroll
       for (int q = 0; q < F32_UNROLL; ++q) {
