@@ -29,6 +29,9 @@ template <int DIM> __host__ __device__ constexpr int node_j(int a) {
 }
 
 constexpr int ASM_WARPS = 8;
+#ifndef NSB_ASM_MIN_CTAS
+#define NSB_ASM_MIN_CTAS 3
+#endif
 
 // The FE tables are read with lane-dependent indices all over both passes; from __constant__
 // memory that serialises (one address per cycle).  Each CTA therefore keeps a copy in shared
@@ -63,8 +66,11 @@ k_cell_context(DevMesh M, AsmParams P, const FeTables* __restrict__ gT, const do
   constexpr int NV = DIM + 1, NN = Fe<DIM>::NN, NQ = Fe<DIM>::NQ, DPC = Fe<DIM>::DPC;
   using C = Ctx<DIM>;
   using Q = QS<DIM>;
-  constexpr int CTXN = NEWTON ? C::N_NEWTON : C::N_LIN;
+  using CL = CtxL<DIM>;
+  constexpr int CTXN = NEWTON ? C::N_NEWTON : CL::N;
   constexpr int WS = NN * DIM * 2 + NV + 4 + NQ * Q::N;     // doubles per warp
+  static_assert(3 * NN * NQ <= NQ * Q::N, "the per-q scratch is reused for c, PQ, QD of the S_ab sums");
+  static_assert(NV * NV <= NN * DIM, "the gathered-velocity scratch is reused for grad lambda products");
   __shared__ double sm_all[ASM_WARPS * WS];
   __shared__ FeTables sT;
   load_tables_to_smem(&sT, gT);
@@ -270,12 +276,71 @@ k_cell_context(DevMesh M, AsmParams P, const FeTables* __restrict__ gT, const do
 
   // ---- phase D: context
   double* co = ctx_out + (size_t)cell * CTXN;
-  if (lane < NV * DIM) co[C::GL + lane] = gl[lane / DIM][lane % DIM];
-  if (lane == 0) { co[C::ABSJ] = absJ; co[C::AVG] = avg; }
-  for (int k = lane; k < NQ * NV; k += 32) co[C::S + k] = sq[(k / NV) * Q::N + Q::S + (k % NV)];
-  if (lane < NQ) co[C::TW + lane] = sq[lane * Q::N + Q::TW];
-  if (NEWTON)
+  if (NEWTON) {
+    if (lane < NV * DIM) co[C::GL + lane] = gl[lane / DIM][lane % DIM];
+    if (lane == 0) { co[C::ABSJ] = absJ; co[C::AVG] = avg; }
+    for (int k = lane; k < NQ * NV; k += 32) co[C::S + k] = sq[(k / NV) * Q::N + Q::S + (k % NV)];
+    if (lane < NQ) co[C::TW + lane] = sq[lane * Q::N + Q::TW];
     for (int k = lane; k < NQ * DIM * DIM; k += 32) co[C::H + k] = sq[(k / (DIM * DIM)) * Q::N + Q::HH + (k % (DIM * DIM))];
+  } else {
+    // Linearised system: finish the quadrature sums of the delta_cd part here, once per cell, so that the
+    // node-row pass (which visits the cell once per node) only combines finished numbers.
+    //   c_a(q)  = u*(q) . grad phi_a(q)
+    //   PQ_a(q) = JxW theta phi_a + tau JxW c_a       QD_a(q) = tau JxW c_a / dt
+    //   S_ab    = |J| Mhat_ab / dt + theta nu tr G_ab + sum_q [PQ_a c_b + QD_a phi_b]      (cpp:744-786)
+    if (lane < NV * DIM) co[CL::GL + lane] = gl[lane / DIM][lane % DIM];
+    if (lane == 0) { co[CL::ABSJ] = absJ; co[CL::AVG] = avg; }
+    constexpr int NAQ = NN * NQ, RAQ = (NAQ + 31) / 32;
+    double cq_[RAQ], pq_[RAQ], qd_[RAQ];
+#pragma unroll
+    for (int r = 0; r < RAQ; ++r) {
+      const int e = lane + 32 * r;
+      cq_[r] = 0.0; pq_[r] = 0.0; qd_[r] = 0.0;
+      if (e < NAQ) {
+        const int a = e / NQ, q = e % NQ;
+        const double* o = sq + q * Q::N;
+        const double ca = T.dco[a][0][q] * o[Q::S + T.idx[a][0]] + T.dco[a][1][q] * o[Q::S + T.idx[a][1]];
+        const double qa = o[Q::TW] * ca;
+        cq_[r] = ca;
+        pq_[r] = o[Q::JW] * P.theta * T.phi[q][a] + qa;
+        qd_[r] = qa * P.inv_dt;
+      }
+    }
+    // products of the barycentric gradients, g_k . g_l (for tr G_ab), in the dead velocity scratch
+    if (lane < NV * NV) {
+      const int k = lane / NV, l = lane % NV;
+      double t = 0.0;
+#pragma unroll
+      for (int m = 0; m < DIM; ++m) t += __ldg(geo + k * DIM + m) * __ldg(geo + l * DIM + m);
+      su[lane] = t;
+    }
+    __syncwarp();                                    // every lane is done reading the per-q scratch
+    double* s_c = sq;
+    double* s_pq = sq + NAQ;
+    double* s_qd = sq + 2 * NAQ;
+#pragma unroll
+    for (int r = 0; r < RAQ; ++r) {
+      const int e = lane + 32 * r;
+      if (e < NAQ) { s_c[e] = cq_[r]; s_pq[e] = pq_[r]; s_qd[e] = qd_[r]; }
+    }
+    __syncwarp();
+    for (int e = lane; e < NN * NN; e += 32) {
+      const int a = e / NN, b = e % NN;
+      double sv_ = 0.0;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) sv_ += s_pq[a * NQ + q] * s_c[b * NQ + q] + s_qd[a * NQ + q] * T.phi[q][b];
+      const int ia0 = T.idx[a][0], ia1 = T.idx[a][1], ib0 = T.idx[b][0], ib1 = T.idx[b][1];
+      const double trG = T.Khat[a][b][0][0] * su[ia0 * NV + ib0] + T.Khat[a][b][0][1] * su[ia0 * NV + ib1] +
+                         T.Khat[a][b][1][0] * su[ia1 * NV + ib0] + T.Khat[a][b][1][1] * su[ia1 * NV + ib1];
+      co[CL::S + e] = absJ * (T.Mhat[a][b] * P.inv_dt + P.theta * P.nu * trG) + sv_;
+    }
+    if (lane < NN) {
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) t += s_qd[lane * NQ + q];
+      co[CL::CA + lane] = t * P.dt;
+    }
+  }
   __syncwarp();
   }   // cell loop
 }
@@ -292,16 +357,18 @@ struct RowOut {
 };
 
 template <int DIM, bool NEWTON>
-__global__ void __launch_bounds__(ASM_WARPS * 32, NEWTON ? 2 : 3)
+__global__ void __launch_bounds__(ASM_WARPS * 32, NEWTON ? 2 : NSB_ASM_MIN_CTAS)
 k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double* __restrict__ cell_rhs,
             const unsigned char* __restrict__ cflag, const double* __restrict__ cval, RowOut out,
             const int* __restrict__ tile_ptr, const FeTables* __restrict__ gT) {
   constexpr int NV = DIM + 1, NN = Fe<DIM>::NN, NQ = Fe<DIM>::NQ, DPC = Fe<DIM>::DPC;
   using C = Ctx<DIM>;
-  constexpr int CTXN = NEWTON ? C::N_NEWTON : C::N_LIN;
+  using CL = CtxL<DIM>;
+  constexpr int CTXN = NEWTON ? C::N_NEWTON : CL::N;
+  constexpr int PUBN = NEWTON ? C::N_NEWTON : CL::HDR;     // context words every lane needs (published in shared memory)
   constexpr int NACT = NN * DIM;                     // active lanes (b,d)
   extern __shared__ double dyn[];
-  __shared__ double s_ctx[ASM_WARPS][CTXN];
+  __shared__ double s_ctx[ASM_WARPS][PUBN];
   __shared__ int s_next;
   __shared__ int s_off[65];
   __shared__ FeTables sT;
@@ -343,14 +410,14 @@ k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double
   const int grp = (lane / DIM) * DIM;                // first lane of this lane's b-group
   double* sc = s_ctx[wid];
   // b-side reference values at this lane's quadrature points q = d, d+DIM, ... (lane-constant)
-  constexpr int QPL = (NQ + DIM - 1) / DIM;
+  constexpr int QPL = NEWTON ? (NQ + DIM - 1) / DIM : 1;
   double phb[QPL], db0[QPL], db1[QPL];
 #pragma unroll
   for (int t = 0; t < QPL; ++t) {
     const int q = d + DIM * t;
-    phb[t] = (q < NQ) ? T.phi[q][b] : 0.0;
-    db0[t] = (q < NQ) ? T.dco[b][0][q] : 0.0;
-    db1[t] = (q < NQ) ? T.dco[b][1][q] : 0.0;
+    phb[t] = (NEWTON && q < NQ) ? T.phi[q][b] : 0.0;
+    db0[t] = (NEWTON && q < NQ) ? T.dco[b][0][q] : 0.0;
+    db1[t] = (NEWTON && q < NQ) ? T.dco[b][1][q] : 0.0;
   }
 
   for (;;) {
@@ -384,18 +451,23 @@ k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double
     // The node's (cell, local index) list is read with one coalesced load per 32 cells; the global
     // data of cell i+1 (context, neighbour ranks, rhs entry) is fetched into registers while cell i is
     // being processed, so no global-memory latency sits on the dependent chain of the cell loop.
-    constexpr int NCW = (CTXN + 31) / 32;                  // context words per lane
+    constexpr int NCW = (PUBN + 31) / 32;                  // published context words per lane
     const long long kc0 = M.n2c_ptr[A];
     const int ncell = (int)(M.n2c_ptr[A + 1] - kc0);
     uint32_t pk_lane = 0;
     double nctx[NCW];
+    double nS = 0.0, nCa = 0.0;                            // linearised: this lane's S_ab, CA_a of the next cell
     int nrb = 0, nrp = 0;
     double nrh = 0.0;
     auto fetch = [&](uint32_t pk) {
       const int cell_ = (int)(pk >> 4), a_ = (int)(pk & 15u);
       const double* cg = ctx + (size_t)cell_ * CTXN;
 #pragma unroll
-      for (int w = 0; w < NCW; ++w) nctx[w] = (lane + 32 * w < CTXN) ? __ldg(cg + lane + 32 * w) : 0.0;
+      for (int w = 0; w < NCW; ++w) nctx[w] = (lane + 32 * w < PUBN) ? __ldg(cg + lane + 32 * w) : 0.0;
+      if (!NEWTON) {
+        nS = __ldg(cg + CL::S + a_ * NN + b);
+        nCa = __ldg(cg + CL::CA + a_);
+      }
       nrb = __ldg(M.rank_uu + ((size_t)cell_ * NN + a_) * NN + b);
       nrp = (lane < DIM * NV) ? (int)__ldg(M.rank_up + ((size_t)cell_ * NN + a_) * NV + lane / DIM) : 0;
       nrh = 0.0;
@@ -414,8 +486,9 @@ k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double
       const int a = (int)(pk & 15u);
       // publish the prefetched data of this cell, then start fetching the next one
 #pragma unroll
-      for (int w = 0; w < NCW; ++w) if (lane + 32 * w < CTXN) sc[lane + 32 * w] = nctx[w];
+      for (int w = 0; w < NCW; ++w) if (lane + 32 * w < PUBN) sc[lane + 32 * w] = nctx[w];
       const int rb = nrb, rp = nrp;
+      const double Slin = nS, Calin = nCa;
       racc += nrh;
       if (ic + 1 < ncell) {
         uint32_t pkn;
@@ -426,26 +499,30 @@ k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double
       __syncwarp();
       const double absJ = sc[C::ABSJ];
       const int ia0 = T.idx[a][0], ia1 = T.idx[a][1];
-      // ---- S_ab: quadrature sum split over the DIM lanes of a b-group, recombined in fixed order
-      double part = 0.0, capart = 0.0;
+      // ---- S_ab (delta_cd part) and CA_a: finished per cell by pass 1 for the linearised system; for Newton the
+      // quadrature sum is split over the DIM lanes of a b-group and recombined in fixed order
+      double Svar = 0.0, Ca = Calin;
+      if (NEWTON) {
+        double part = 0.0, capart = 0.0;
 #pragma unroll
-      for (int t = 0; t < QPL; ++t) {
-        const int q = d + DIM * t;
-        if (q < NQ) {
-          const double* s = sc + C::S + q * NV;
-          const double tw = sc[C::TW + q];
-          const double pha = T.phi[q][a];
-          const double ca = T.dco[a][0][q] * s[ia0] + T.dco[a][1][q] * s[ia1];
-          const double cb = db0[t] * s[ib0] + db1[t] * s[ib1];
-          const double Pa = T.w[q] * absJ * P.theta * pha;
-          const double Qa = tw * ca;
-          part += Pa * cb + Qa * (phb[t] * P.inv_dt + cb);
-          capart += Qa;
+        for (int t = 0; t < QPL; ++t) {
+          const int q = d + DIM * t;
+          if (q < NQ) {
+            const double* s = sc + C::S + q * NV;
+            const double tw = sc[C::TW + q];
+            const double pha = T.phi[q][a];
+            const double ca = T.dco[a][0][q] * s[ia0] + T.dco[a][1][q] * s[ia1];
+            const double cb = db0[t] * s[ib0] + db1[t] * s[ib1];
+            const double Pa = T.w[q] * absJ * P.theta * pha;
+            const double Qa = tw * ca;
+            part += Pa * cb + Qa * (phb[t] * P.inv_dt + cb);
+            capart += Qa;
+          }
         }
-      }
-      double Svar = 0.0, Ca = 0.0;
+        Ca = 0.0;
 #pragma unroll
-      for (int k = 0; k < DIM; ++k) { Svar += shfl_d(part, grp + k); Ca += shfl_d(capart, grp + k); }
+        for (int k = 0; k < DIM; ++k) { Svar += shfl_d(part, grp + k); Ca += shfl_d(capart, grp + k); }
+      }
       // ---- G^{cd}_ab for this lane's column d, all rows c
       const double gb0 = sc[C::GL + ib0 * DIM + d], gb1 = sc[C::GL + ib1 * DIM + d];
       const double t0 = T.Khat[a][b][0][0] * gb0 + T.Khat[a][b][0][1] * gb1;
@@ -453,16 +530,15 @@ k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double
       double G[DIM];
 #pragma unroll
       for (int c = 0; c < DIM; ++c) G[c] = absJ * (sc[C::GL + ia0 * DIM + c] * t0 + sc[C::GL + ia1 * DIM + c] * t1);
-      double Gdd = 0.0;
+      double Sab = Slin;
+      if (NEWTON) {
+        double Gdd = 0.0;
 #pragma unroll
-      for (int c = 0; c < DIM; ++c) if (c == d) Gdd = G[c];
-      double trG = 0.0;
+        for (int c = 0; c < DIM; ++c) if (c == d) Gdd = G[c];
+        double trG = 0.0;
 #pragma unroll
-      for (int k = 0; k < DIM; ++k) trG += shfl_d(Gdd, grp + k);
-      const double Sab = absJ * T.Mhat[a][b] * P.inv_dt + P.theta * P.nu * trG + Svar;
-      if (!NEWTON && out.s_rows && act && d == 0) {
-        const long long p = kc0 + ic;
-        out.s_rows[((size_t)(p >> 5) * (NN / 2) + (size_t)(b >> 1)) * 64 + (size_t)(p & 31) * 2 + (size_t)(b & 1)] = (float)Sab;
+        for (int k = 0; k < DIM; ++k) trG += shfl_d(Gdd, grp + k);
+        Sab = absJ * T.Mhat[a][b] * P.inv_dt + P.theta * P.nu * trG + Svar;
       }
       double val[DIM];
 #pragma unroll

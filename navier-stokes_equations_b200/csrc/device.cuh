@@ -69,6 +69,21 @@ template <int DIM> struct Ctx {
   static constexpr int N_NEWTON = ((H + NQ * DIM * DIM + 7) / 8) * 8;
 };
 
+// Context of the LINEARISED system: the quadrature sums are finished per cell in pass 1, pass 2 only reads
+//   S_ab = |J| Mhat_ab / dt + theta nu tr G_ab + sum_q [Pa cb + Qa (phi_b / dt + cb)]   (the delta_cd part of the block)
+//   CA_a = sum_q tau JxW (u* . grad phi_a)                                             (SUPG pressure column)
+template <int DIM> struct CtxL {
+  static constexpr int NV = DIM + 1;
+  static constexpr int NN = Fe<DIM>::NN;
+  static constexpr int GL = 0;                          // grad lambda [NV][DIM]
+  static constexpr int ABSJ = NV * DIM;
+  static constexpr int AVG = ABSJ + 1;
+  static constexpr int HDR = ((AVG + 1 + 7) / 8) * 8;   // 16 (3-D), 8 (2-D)
+  static constexpr int S = HDR;                         // S[a][b]
+  static constexpr int CA = S + NN * NN;
+  static constexpr int N = ((CA + NN + 7) / 8) * 8;     // 128 (3-D), 56 (2-D)
+};
+
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(NSB_FULL, v, src); }
 
 __device__ __forceinline__ double warp_sum_fixed(double v) {

@@ -327,7 +327,7 @@ template <int DIM> void launch_assemble(nsb_ctx* c, bool newton) {
   P.use_supg = c->par.use_supg;
   P.gamma = c->par.use_supg ? c->par.gamma : 0.0;
   P.first_order_ustar = c->par.first_order_ustar;
-  const int stride = newton ? Ctx<DIM>::N_NEWTON : Ctx<DIM>::N_LIN;
+  const int stride = newton ? Ctx<DIM>::N_NEWTON : CtxL<DIM>::N;
   if ((int)c->ctx_stride < stride) {
     c->ctx.alloc((size_t)c->S.nc * stride);
     c->ctx_stride = stride;
