@@ -59,8 +59,11 @@ template <int DIM> struct QS {
 // ------------------------------------------------------------------------------------
 // pass 1
 // ------------------------------------------------------------------------------------
+#ifndef NSB_CTX_MIN_CTAS
+#define NSB_CTX_MIN_CTAS 2
+#endif
 template <int DIM, bool NEWTON>
-__global__ void __launch_bounds__(ASM_WARPS * 32)
+__global__ void __launch_bounds__(ASM_WARPS * 32, NSB_CTX_MIN_CTAS)
 k_cell_context(DevMesh M, AsmParams P, const FeTables* __restrict__ gT, const double* __restrict__ vecA,
                const double* __restrict__ vecB, double* __restrict__ ctx_out, double* __restrict__ cell_rhs) {
   constexpr int NV = DIM + 1, NN = Fe<DIM>::NN, NQ = Fe<DIM>::NQ, DPC = Fe<DIM>::DPC;
@@ -324,15 +327,33 @@ k_cell_context(DevMesh M, AsmParams P, const FeTables* __restrict__ gT, const do
       if (e < NAQ) { s_c[e] = cq_[r]; s_pq[e] = pq_[r]; s_qd[e] = qd_[r]; }
     }
     __syncwarp();
-    for (int e = lane; e < NN * NN; e += 32) {
-      const int a = e / NN, b = e % NN;
-      double sv_ = 0.0;
+    // 2 x 2 register tiles of S: one lane per tile, four independent accumulation chains, half the operand loads
+    constexpr int NT = NN / 2;
+    static_assert(NN % 2 == 0 && NT * NT <= 32, "one lane per 2x2 tile of S");
+    if (lane < NT * NT) {
+      const int a0 = 2 * (lane / NT), b0 = 2 * (lane % NT);
+      double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) sv_ += s_pq[a * NQ + q] * s_c[b * NQ + q] + s_qd[a * NQ + q] * T.phi[q][b];
-      const int ia0 = T.idx[a][0], ia1 = T.idx[a][1], ib0 = T.idx[b][0], ib1 = T.idx[b][1];
-      const double trG = T.Khat[a][b][0][0] * su[ia0 * NV + ib0] + T.Khat[a][b][0][1] * su[ia0 * NV + ib1] +
-                         T.Khat[a][b][1][0] * su[ia1 * NV + ib0] + T.Khat[a][b][1][1] * su[ia1 * NV + ib1];
-      co[CL::S + e] = absJ * (T.Mhat[a][b] * P.inv_dt + P.theta * P.nu * trG) + sv_;
+      for (int q = 0; q < NQ; ++q) {
+        const double pa[2] = {s_pq[a0 * NQ + q], s_pq[(a0 + 1) * NQ + q]};
+        const double qa[2] = {s_qd[a0 * NQ + q], s_qd[(a0 + 1) * NQ + q]};
+        const double cb[2] = {s_c[b0 * NQ + q], s_c[(b0 + 1) * NQ + q]};
+        const double fb[2] = {T.phi[q][b0], T.phi[q][b0 + 1]};
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) acc[i][j] += pa[i] * cb[j] + qa[i] * fb[j];
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int a = a0 + i, b = b0 + j;
+          const int ia0 = T.idx[a][0], ia1 = T.idx[a][1], ib0 = T.idx[b][0], ib1 = T.idx[b][1];
+          const double trG = T.Khat[a][b][0][0] * su[ia0 * NV + ib0] + T.Khat[a][b][0][1] * su[ia0 * NV + ib1] +
+                             T.Khat[a][b][1][0] * su[ia1 * NV + ib0] + T.Khat[a][b][1][1] * su[ia1 * NV + ib1];
+          co[CL::S + a * NN + b] = absJ * (T.Mhat[a][b] * P.inv_dt + P.theta * P.nu * trG) + acc[i][j];
+        }
     }
     if (lane < NN) {
       double t = 0.0;
@@ -539,6 +560,10 @@ k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double
 #pragma unroll
         for (int k = 0; k < DIM; ++k) trG += shfl_d(Gdd, grp + k);
         Sab = absJ * T.Mhat[a][b] * P.inv_dt + P.theta * P.nu * trG + Svar;
+      } else if (out.s_rows && act && d == 0) {
+        // row a of S_e for the element-wise velocity operator (ebe.cuh), blocked by 32 pairs
+        const long long p = kc0 + ic;
+        out.s_rows[((size_t)(p >> 5) * (NN / 2) + (size_t)(b >> 1)) * 64 + (size_t)(p & 31) * 2 + (size_t)(b & 1)] = (float)Sab;
       }
       double val[DIM];
 #pragma unroll
