@@ -30,7 +30,7 @@ template <int DIM> __host__ __device__ constexpr int node_j(int a) {
 
 constexpr int ASM_WARPS = 8;
 #ifndef NSB_ASM_MIN_CTAS
-#define NSB_ASM_MIN_CTAS 3
+#define NSB_ASM_MIN_CTAS 4
 #endif
 
 // The FE tables are read with lane-dependent indices all over both passes; from __constant__
