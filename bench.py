@@ -351,8 +351,8 @@ def main():
             if k in kernels:
                 kernels[k]["algorithmic_GBps"] = round(bytes_alg[k] / (kernels[k]["ms_avg"] * 1e-3) / 1e9, 1)
         if not args.no_cpu_baseline and world == 1:
-            cells_s, secs, its_s, ok_s, thr = cpu_step_sample(repeats=1)
-            line["cpu_baseline"] = cpu_baseline_entry(cells_s, secs[0], its_s, ok_s, thr, hs.n_cells)
+            cells_s, secs, its_s, ok_s, thr = cpu_step_sample(repeats=3)      # first pass warms the caches / thread pool
+            line["cpu_baseline"] = cpu_baseline_entry(cells_s, float(np.mean(secs[1:])), its_s, ok_s, thr, hs.n_cells)
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
