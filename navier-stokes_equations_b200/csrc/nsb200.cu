@@ -278,39 +278,41 @@ size_t vals_f_size(const nsb_ctx* c) {
 }
 
 // ---- halo exchange of one local vector (ghost tail refreshed from the owners) -----------
-void halo_exchange(nsb_ctx* c, double* v) {
+void halo_exchange(nsb_ctx* c, double* v, bool with_pressure = true) {
   if (c->nranks == 1) return;
   const Structure& S = c->S;
-  // pack + grouped send/recv: ghosts are stored per owner contiguously, so receives land in place
+  // One pack kernel for all peers (+ one for the pressure DoFs), then a grouped send/recv: ghosts are stored per
+  // owner contiguously, so receives land in place.  The velocity polynomial only needs velocity ghosts.
   auto& B = c->halo;
   if (B.empty()) {
+    auto b = std::make_unique<HaloBuf>();
+    std::vector<int> uo, po;
     for (size_t k = 0; k < S.peer.size(); ++k) {
-      auto b = std::make_unique<HaloBuf>();
-      std::vector<int> uo(S.send_nodes[k].size()), po(S.send_pids[k].size());
-      for (size_t i = 0; i < uo.size(); ++i) uo[i] = (int)S.node_xoff(S.send_nodes[k][i]);
-      for (size_t i = 0; i < po.size(); ++i) po[i] = (int)S.pid_xoff(S.send_pids[k][i]);
-      b->uoff.upload(uo, c->stream); b->poff.upload(po, c->stream);
-      CK(cudaStreamSynchronize(c->stream));
-      b->u.alloc(uo.size() * S.dim); b->p.alloc(po.size());
-      B.push_back(std::move(b));
+      for (int n : S.send_nodes[k]) uo.push_back((int)S.node_xoff(n));
+      for (int q : S.send_pids[k]) po.push_back((int)S.pid_xoff(q));
     }
+    b->uoff.upload(uo, c->stream); b->poff.upload(po, c->stream);
+    CK(cudaStreamSynchronize(c->stream));
+    b->u.alloc(uo.size() * S.dim); b->p.alloc(po.size());
+    B.push_back(std::move(b));
   }
-  for (size_t k = 0; k < S.peer.size(); ++k) {
-    const int nu = (int)S.send_nodes[k].size(), np = (int)S.send_pids[k].size();
-    if (nu) { k_gather_nodes<<<nblk((long long)nu * S.dim, 256), 256, 0, c->stream>>>(nu, S.dim, B[k]->uoff.p, v, B[k]->u.p); c->launch_check(); }
-    if (np) { k_gather<<<nblk(np, 256), 256, 0, c->stream>>>(np, B[k]->poff.p, v, B[k]->p.p); c->launch_check(); }
-  }
+  HaloBuf& H = *B[0];
+  const long long tu = (long long)H.uoff.n, tp = (long long)H.poff.n;
+  if (tu) { k_gather_nodes<<<nblk(tu * S.dim, 256), 256, 0, c->stream>>>((int)tu, S.dim, H.uoff.p, v, H.u.p); c->launch_check(); }
+  if (with_pressure && tp) { k_gather<<<nblk(tp, 256), 256, 0, c->stream>>>((int)tp, H.poff.p, v, H.p.p); c->launch_check(); }
   CKN(g_nccl.GroupStart());
   long long uoff = S.n_own_dofs(), poff = S.n_own_dofs() + (long long)S.dim * S.nn_ghost;
+  size_t su = 0, sp = 0;
   for (size_t k = 0; k < S.peer.size(); ++k) {
     const int peer = S.peer[k];
     const size_t nu = S.send_nodes[k].size() * S.dim, np = S.send_pids[k].size();
-    if (nu) CKN(g_nccl.Send(B[k]->u.p, nu, ncclDouble, peer, c->comm, c->stream));
-    if (np) CKN(g_nccl.Send(B[k]->p.p, np, ncclDouble, peer, c->comm, c->stream));
+    if (nu) CKN(g_nccl.Send(H.u.p + su, nu, ncclDouble, peer, c->comm, c->stream));
+    if (with_pressure && np) CKN(g_nccl.Send(H.p.p + sp, np, ncclDouble, peer, c->comm, c->stream));
     const size_t ru = (size_t)S.recv_node_count[k] * S.dim, rp = (size_t)S.recv_pid_count[k];
     if (ru) CKN(g_nccl.Recv(v + uoff, ru, ncclDouble, peer, c->comm, c->stream));
-    if (rp) CKN(g_nccl.Recv(v + poff, rp, ncclDouble, peer, c->comm, c->stream));
+    if (with_pressure && rp) CKN(g_nccl.Recv(v + poff, rp, ncclDouble, peer, c->comm, c->stream));
     uoff += ru; poff += rp;
+    su += nu; sp += np;
   }
   CKN(g_nccl.GroupEnd());
 }
@@ -473,7 +475,7 @@ void setup_F_poly(nsb_ctx* c) {
     const double* xin = vk;
     if (c->nranks > 1) {
       CK(cudaMemcpyAsync(c->w_pin.p, vk, nu * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-      halo_exchange(c, c->w_pin.p);
+      halo_exchange(c, c->w_pin.p, false);
       xin = c->w_pin.p;
     }
     spmv_vel<2>(c, xin, w, nullptr, nullptr, PolyCoef{});
@@ -600,17 +602,17 @@ void apply_F_poly(nsb_ctx* c, const double* x) {
         c->launch_check();
       } else {
         // poly += prod/theta ; prod <- prod - B prod / theta
-        halo_exchange(c, prod);
+        halo_exchange(c, prod, false);
         spmv_vel<3>(c, prod, other, prod, poly, PolyCoef{1.0, -1.0 / a, 1.0 / a, 0.0});
         std::swap(prod, other);
       }
     } else {
       const double m2 = a * a + b * b;
       // tmp = 2a prod - B prod ; poly += tmp/m2 ; prod <- prod - B tmp / m2
-      halo_exchange(c, prod);
+      halo_exchange(c, prod, false);
       spmv_vel<3>(c, prod, tmp, prod, poly, PolyCoef{2.0 * a, -1.0, 0.0, 1.0 / m2});
       if (!last) {
-        halo_exchange(c, tmp);
+        halo_exchange(c, tmp, false);
         spmv_vel<3>(c, tmp, other, prod, poly, PolyCoef{1.0, -1.0 / m2, 0.0, 0.0});
         std::swap(prod, other);
       }
@@ -1246,6 +1248,7 @@ int nsb_upload_mesh(nsb_handle c, int64_t n_vertices, const double* coords, int6
   CK(cudaStreamSynchronize(st));
   c->have_mesh = true; c->have_matrix = false; c->have_pressure = false;
   c->eig_init = false; c->poly_roots.clear(); c->solves = 0; c->V_cap = 0;
+  c->halo.clear();                 // pack lists of the previous mesh
   return 0;
   NSB_CATCH(c)
 }
