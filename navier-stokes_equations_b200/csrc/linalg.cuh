@@ -339,16 +339,19 @@ using F32X = double;
 #endif
 constexpr int F32_UNROLL = NSB_F32_UNROLL;  // 3 x 32 columns covers the 81 columns of a line node in one trip
 
-template <int DIM, int MODE>
+// LISTED: the CTA's tile is tile_list[blockIdx.x] -- used by the multi-GPU path to run the tiles that read no
+// ghost entries while the halo exchange is in flight, and the boundary tiles afterwards.
+template <int DIM, int MODE, bool LISTED = false>
 __global__ void __launch_bounds__(SPMV_WARPS * 32)
 k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __restrict__ fv,
                const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ u,
-               double* __restrict__ poly, const double* __restrict__ dinv, PolyCoef pc) {
+               double* __restrict__ poly, const double* __restrict__ dinv, PolyCoef pc,
+               const int* __restrict__ tile_list = nullptr) {
   using V = typename F32Vec<DIM>::type;
   __shared__ TileSmem<DIM, F32X> T;
   const int lane = threadIdx.x & 31;
   int n0, n1;
-  stage_tile<DIM, false, F32X>(M, TL, blockIdx.x, x, T, n0, n1);
+  stage_tile<DIM, false, F32X>(M, TL, LISTED ? __ldg(tile_list + blockIdx.x) : (int)blockIdx.x, x, T, n0, n1);
   for (;;) {
     int slot = 0;
     if (lane == 0) slot = atomicAdd(&T.next, 1);

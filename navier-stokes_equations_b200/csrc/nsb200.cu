@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -228,6 +229,13 @@ struct nsb_ctx {
   double Mp_lmax = 1.0;
   std::vector<std::unique_ptr<DevLevel>> amg;
   std::vector<std::unique_ptr<HaloBuf>> halo;
+  // halo / compute overlap of the velocity polynomial (multi-GPU): tiles that read no ghost entry run while the
+  // exchange is in flight on comm_stream, the boundary tiles after it
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;
+  DBuf<int> d_tiles_int, d_tiles_bnd;
+  int n_tiles_int = 0, n_tiles_bnd = 0;
+  bool overlap = false;
   double* pin = nullptr;           // pinned staging buffer for host <-> device vector traffic (n_tot doubles)
   DBuf<double> coarse_inv;
   int coarse_n = 0;
@@ -317,6 +325,31 @@ void halo_exchange(nsb_ctx* c, double* v, bool with_pressure = true) {
   CKN(g_nccl.GroupEnd());
 }
 
+// velocity-only exchange started on the communication stream; the caller waits on ev_halo before it reads ghosts
+void halo_start_velocity(nsb_ctx* c, double* v) {
+  const Structure& S = c->S;
+  if (c->halo.empty()) { halo_exchange(c, v, false); CK(cudaEventRecord(c->ev_halo, c->stream)); return; }   // builds the pack lists
+  HaloBuf& H = *c->halo[0];
+  const long long tu = (long long)H.uoff.n;
+  if (tu) { k_gather_nodes<<<nblk(tu * S.dim, 256), 256, 0, c->stream>>>((int)tu, S.dim, H.uoff.p, v, H.u.p); c->launch_check(); }
+  CK(cudaEventRecord(c->ev_pack, c->stream));
+  CK(cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
+  CKN(g_nccl.GroupStart());
+  long long uoff = S.n_own_dofs();
+  size_t su = 0;
+  for (size_t k = 0; k < S.peer.size(); ++k) {
+    const int peer = S.peer[k];
+    const size_t nu = S.send_nodes[k].size() * S.dim;
+    if (nu) CKN(g_nccl.Send(H.u.p + su, nu, ncclDouble, peer, c->comm, c->comm_stream));
+    const size_t ru = (size_t)S.recv_node_count[k] * S.dim;
+    if (ru) CKN(g_nccl.Recv(v + uoff, ru, ncclDouble, peer, c->comm, c->comm_stream));
+    uoff += ru;
+    su += nu;
+  }
+  CKN(g_nccl.GroupEnd());
+  CK(cudaEventRecord(c->ev_halo, c->comm_stream));
+}
+
 void allreduce_sum(nsb_ctx* c, double* dbuf, int n) {
   if (c->nranks == 1) return;
   CKN(g_nccl.AllReduce(dbuf, dbuf, n, ncclDouble, ncclSum, c->comm, c->stream));
@@ -392,6 +425,29 @@ void spmv_vel(nsb_ctx* c, const double* x, double* y, const double* u, double* p
     else k_spmv_vel<3, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, c->vals.p, x, y, u, poly, c->dinv.p, pc);
   }
   c->launch_check();
+  c->prof.end(id, c->stream);
+}
+
+// one root of the velocity polynomial on a vector whose ghosts are stale: exchange + F application, overlapped when
+// the fp32 assembled operator is in use on several GPUs
+void halo_spmv_vel3(nsb_ctx* c, double* x, double* y, const double* u, double* poly, PolyCoef pc) {
+  const bool ovl = c->nranks > 1 && c->overlap && c->vals_f.p && !c->ebe_valid && c->n_tiles_int > 0;
+  if (!ovl) {
+    halo_exchange(c, x, false);
+    spmv_vel<3>(c, x, y, u, poly, pc);
+    return;
+  }
+  halo_start_velocity(c, x);
+  size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
+  if (c->dim == 2) k_spmv_vel_f32<2, 3, true><<<c->n_tiles_int, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float2*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc, c->d_tiles_int.p);
+  else k_spmv_vel_f32<3, 3, true><<<c->n_tiles_int, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float4*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc, c->d_tiles_int.p);
+  c->launch_check();
+  CK(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+  if (c->n_tiles_bnd > 0) {
+    if (c->dim == 2) k_spmv_vel_f32<2, 3, true><<<c->n_tiles_bnd, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float2*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc, c->d_tiles_bnd.p);
+    else k_spmv_vel_f32<3, 3, true><<<c->n_tiles_bnd, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float4*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc, c->d_tiles_bnd.p);
+    c->launch_check();
+  }
   c->prof.end(id, c->stream);
 }
 
@@ -602,18 +658,15 @@ void apply_F_poly(nsb_ctx* c, const double* x) {
         c->launch_check();
       } else {
         // poly += prod/theta ; prod <- prod - B prod / theta
-        halo_exchange(c, prod, false);
-        spmv_vel<3>(c, prod, other, prod, poly, PolyCoef{1.0, -1.0 / a, 1.0 / a, 0.0});
+        halo_spmv_vel3(c, prod, other, prod, poly, PolyCoef{1.0, -1.0 / a, 1.0 / a, 0.0});
         std::swap(prod, other);
       }
     } else {
       const double m2 = a * a + b * b;
       // tmp = 2a prod - B prod ; poly += tmp/m2 ; prod <- prod - B tmp / m2
-      halo_exchange(c, prod, false);
-      spmv_vel<3>(c, prod, tmp, prod, poly, PolyCoef{2.0 * a, -1.0, 0.0, 1.0 / m2});
+      halo_spmv_vel3(c, prod, tmp, prod, poly, PolyCoef{2.0 * a, -1.0, 0.0, 1.0 / m2});
       if (!last) {
-        halo_exchange(c, tmp, false);
-        spmv_vel<3>(c, tmp, other, prod, poly, PolyCoef{1.0, -1.0 / m2, 0.0, 0.0});
+        halo_spmv_vel3(c, tmp, other, prod, poly, PolyCoef{1.0, -1.0 / m2, 0.0, 0.0});
         std::swap(prod, other);
       }
     }
@@ -859,7 +912,7 @@ void build_tiles(nsb_ctx* c) {
   // SpMV tiles: consecutive nodes with bounded staged index count and bounded UNIQUE neighbour sets
   {
     const int ntot = S.nn_own + S.nn_ghost, ptot = S.np_own + S.np_ghost;
-    std::vector<int> sp, uptr, uxoff, pptr, pxoff;
+    std::vector<int> sp, uptr, uxoff, pptr, pxoff, tiles_int, tiles_bnd;
     std::vector<unsigned short> nloc(S.nbr.size()), ploc(S.pnbr.size());
     std::vector<int> stamp(ntot, -1), pstamp(ptot, -1), posn(ntot, 0), posp(ptot, 0);
     sp.push_back(0); uptr.push_back(0); pptr.push_back(0);
@@ -893,6 +946,9 @@ void build_tiles(nsb_ctx* c) {
         for (int64_t k = S.nbr_ptr[B]; k < S.nbr_ptr[B + 1]; ++k) nloc[k] = (unsigned short)posn[S.nbr[k]];
         for (int64_t k = S.pnbr_ptr[B]; k < S.pnbr_ptr[B + 1]; ++k) ploc[k] = (unsigned short)posp[S.pnbr[k]];
       }
+      bool reads_ghost = false;
+      for (int n : U) reads_ghost |= (n >= S.nn_own);
+      (reads_ghost ? tiles_bnd : tiles_int).push_back(tile);
       sp.push_back(A); uptr.push_back((int)uxoff.size()); pptr.push_back((int)pxoff.size());
       ++tile;
     }
@@ -950,6 +1006,8 @@ void build_tiles(nsb_ctx* c) {
       c->ebe_valid = false;
     }
     c->d_stile_ptr.upload(sp, c->stream);
+    c->n_tiles_int = (int)tiles_int.size(); c->n_tiles_bnd = (int)tiles_bnd.size();
+    c->d_tiles_int.upload(tiles_int, c->stream); c->d_tiles_bnd.upload(tiles_bnd, c->stream);
     c->d_suniq_ptr.upload(uptr, c->stream); c->d_suniq_xoff.upload(uxoff, c->stream);
     c->d_spuniq_ptr.upload(pptr, c->stream); c->d_spuniq_xoff.upload(pxoff, c->stream);
     c->d_nbr_loc.upload(nloc, c->stream); c->d_pnbr_loc.upload(ploc, c->stream);
@@ -1102,6 +1160,9 @@ int nsb_destroy(nsb_handle c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm_stream) { cudaStreamSynchronize(c->comm_stream); cudaStreamDestroy(c->comm_stream); }
+  if (c->ev_pack) cudaEventDestroy(c->ev_pack);
+  if (c->ev_halo) cudaEventDestroy(c->ev_halo);
   if (c->pin) cudaFreeHost(c->pin);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   if (c->t0) cudaEventDestroy(c->t0);
@@ -1135,6 +1196,11 @@ int nsb_comm_init(nsb_handle c, int rank, int nranks, const void* uid) {
     ncclUniqueId id;
     std::memcpy(&id, uid, sizeof(id));
     CKN(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+    CK(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+    const char* ov = std::getenv("NSB200_OVERLAP");          // 0 disables the halo / compute overlap
+    c->overlap = !(ov && ov[0] == '0');
   }
   c->rank = rank; c->nranks = nranks;
   return 0;
