@@ -6,7 +6,8 @@
 //
 // Two passes, both deterministic and atomics-free (DESIGN.md "Assembly"):
 //   1. k_cell_context : one warp per cell.  Evaluates u^n, u^{n-1} (or u^k, p^k), u*, tau at the
-//      quadrature points, writes a 512-byte cell context and the cell's rhs vector.
+//      quadrature points, writes the cell's rhs vector and its context: for the linearised system
+//      the finished scalar block S_ab (CtxL, 1 KB), for Newton the per-point data (Ctx).
 //   2. k_node_rows    : one warp per OWNED P2 node.  Walks the node's cells in ascending order,
 //      computes the dim (+1) local matrix rows of that node exploiting the component-block
 //      structure  A[(a,c),(b,d)] = delta_cd S_ab + gamma G^{cd}_ab (+ T^{cd}_ab for Newton),

@@ -55,7 +55,7 @@ struct AsmParams {
 };
 
 
-// Context written per cell by the first pass and consumed by the node-row pass.
+// Context written per cell by the first pass and consumed by the node-row pass (Newton system: per-point data).
 template <int DIM> struct Ctx {
   static constexpr int NV = DIM + 1;
   static constexpr int NQ = Fe<DIM>::NQ;
@@ -65,7 +65,6 @@ template <int DIM> struct Ctx {
   static constexpr int S = ABSJ + 2;              // s[q][k] = u*(q) . grad lambda_k
   static constexpr int TW = S + NQ * NV;          // tau(q) * JxW(q)   (0 without SUPG)
   static constexpr int H = TW + NQ;               // extra (Newton): grad u^k(q) [NQ][DIM][DIM]
-  static constexpr int N_LIN = ((H + 7) / 8) * 8; // 64 (3-D), 40 (2-D)
   static constexpr int N_NEWTON = ((H + NQ * DIM * DIM + 7) / 8) * 8;
 };
 
