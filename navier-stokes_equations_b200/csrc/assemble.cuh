@@ -633,17 +633,8 @@ k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double
         // fp32 copy of the velocity block, one vector per column holding all DIM rows
         constexpr int W = (DIM == 3) ? 4 : 2;
         float* o = out.vals_f + ((long long)DIM * nptr[0] + k) * W;
-#ifdef NSB_F32_PLANAR
-        if (DIM == 3) {
-          // dense row planes: [row][column] floats per node, no padding (experiment, see profiles/README.md)
-          float* pl = out.vals_f + (long long)DIM * DIM * nptr[0];
-          pl[k] = (float)acc[k]; pl[DIM * nb + k] = (float)acc[len + k]; pl[2 * DIM * nb + k] = (float)acc[2 * len + k];
-        } else
-#else
         if (DIM == 3) *reinterpret_cast<float4*>(o) = make_float4((float)acc[k], (float)acc[len + k], (float)acc[2 * len + k], 0.f);
-        else
-#endif
-          *reinterpret_cast<float2*>(o) = make_float2((float)acc[k], (float)acc[len + k]);
+        else *reinterpret_cast<float2*>(o) = make_float2((float)acc[k], (float)acc[len + k]);
       }
       if (isv) {
         double v = acc[DIM * len + k];

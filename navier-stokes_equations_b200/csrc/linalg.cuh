@@ -330,13 +330,9 @@ template <> struct F32Vec<2> { using type = float2; };
 #ifndef NSB_F32_UNROLL
 #define NSB_F32_UNROLL 3
 #endif
-// storage of the staged x inside k_spmv_vel_f32: double keeps the operator exactly linear; float halves the
-// shared-memory gather traffic (experiment, see profiles/README.md)
-#ifdef NSB_XS32
-using F32X = float;
-#else
+// storage of the staged x inside k_spmv_vel_f32: double keeps the operator exactly linear (staging x as float was
+// measured slower, see profiles/README.md)
 using F32X = double;
-#endif
 constexpr int F32_UNROLL = NSB_F32_UNROLL;  // 3 x 32 columns covers the 81 columns of a line node in one trip
 
 // LISTED: the CTA's tile is tile_list[blockIdx.x] -- used by the multi-GPU path to run the tiles that read no
@@ -367,9 +363,6 @@ k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __rest
     double sum[DIM];
 #pragma unroll
     for (int c = 0; c < DIM; ++c) sum[c] = 0.0;
-#ifdef NSB_F32_PLANAR
-    const float* pl = reinterpret_cast<const float*>(fv) + (long long)DIM * DIM * d.nbr0;
-#endif
     for (int k0 = 0; k0 < nbd; k0 += 32 * F32_UNROLL) {
       V v[F32_UNROLL];
       double xv[F32_UNROLL];
@@ -378,16 +371,7 @@ k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __rest
         const int k = k0 + 32 * q + lane;
         v[q] = V();
         xv[q] = 0.0;
-        if (k < nbd) {
-#ifdef NSB_F32_PLANAR
-          if (DIM == 3) {
-            v[q].x = NSB_STREAM_LOAD(pl + k); v[q].y = NSB_STREAM_LOAD(pl + nbd + k);
-            reinterpret_cast<float*>(&v[q])[DIM - 1] = NSB_STREAM_LOAD(pl + 2 * nbd + k);
-          } else
-#endif
-            v[q] = NSB_STREAM_LOAD(rp + k);
-          xv[q] = (double)T.xs[(int)nx[k / DIM] * DIM + k % DIM];
-        }
+        if (k < nbd) { v[q] = NSB_STREAM_LOAD(rp + k); xv[q] = (double)T.xs[(int)nx[k / DIM] * DIM + k % DIM]; }
       }
 #pragma unroll
       for (int q = 0; q < F32_UNROLL; ++q) {
