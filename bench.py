@@ -104,7 +104,8 @@ def measured_peak():
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle's restatement of one time step on a bounded sample of the workload
 # ------------------------------------------------------------------------------------------------
-SAMPLE_LC = 0.025       # cylinder mesh size of the CPU sample mesh (52 704 tets, 236 789 DoFs)
+# cylinder mesh size of the CPU sample mesh (0.025: 52 704 tets, 236 789 DoFs); the override exists for the tests
+SAMPLE_LC = float(os.environ.get("NSB_BENCH_SAMPLE_LC", "0.025"))
 
 
 def cpu_step_sample(repeats=1):
