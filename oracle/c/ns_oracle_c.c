@@ -5,6 +5,7 @@
  * reference itself cannot be built here).  This file restates, in plain C with OpenMP over cells / rows /
  * row blocks, what the reference executes per time step on the CPU:
  *
+ *   nso_assemble_newton       NavierStokes<dim>::assemble_newton_system()      reference src/classes/NavierStokes.cpp:278-539
  *   nso_assemble_linearized   NavierStokes<dim>::assemble_linearized_system()  reference src/classes/NavierStokes.cpp:569-831
  *                             (per-cell, per-q, per-(i,j) loops on vector-valued shape functions exactly as
  *                             written there, tau recomputed inside the loops like cpp:725-729 / 769-773) and
@@ -84,11 +85,13 @@ static int64_t csr_find(const int64_t *rowptr, const int32_t *col, int64_t row, 
 }
 
 /* ------------------------------------------------------------------ assembly (reference loops) */
-void nso_assemble_linearized(int dim, int64_t n_cells, const double *points, const int32_t *cells, const int32_t *cell_dofs,
-                             int64_t N, const int64_t *rowptr, const int32_t *col, const unsigned char *is_c,
-                             const double *cval, const double *sol_old, const double *sol_old_old, double deltat,
-                             double theta, double nu, int use_supg, double gamma, int first_order_ustar, double *A,
-                             double *b, double *Mp, double *Kp) {
+/* newton == 0: assemble_linearized_system (cpp:569-831), vectors (u^n, u^{n-1});
+ * newton == 1: assemble_newton_system (cpp:278-539), vectors (u^k, u^n) -- Jacobian and minus the residual. */
+static void assemble_impl(int newton, int dim, int64_t n_cells, const double *points, const int32_t *cells,
+                          const int32_t *cell_dofs, int64_t N, const int64_t *rowptr, const int32_t *col,
+                          const unsigned char *is_c, const double *cval, const double *sol_old, const double *sol_old_old,
+                          double deltat, double theta, double nu, int use_supg, double gamma, int first_order_ustar,
+                          double *A, double *b, double *Mp, double *Kp) {
   fe_t T;
   fe_init(&T, dim);
   const int K = T.dpc, NV = T.nv, NQ = T.nq;
@@ -156,6 +159,90 @@ void nso_assemble_linearized(int dim, int64_t n_cells, const double *points, con
           phi_p[k] = T.lam[q][a];
           for (int m = 0; m < dim; ++m) grad_phi_p[k][m] = gl[a][m];
         }
+      }
+      if (newton) {
+        /* current iterate u^k, p^k (sol_old here) and previous time level u^n (sol_old_old here)   cpp:344-375 */
+        double u_k[3] = {0}, u_o[3] = {0}, gu_k[3][3] = {{0}}, gu_o[3][3] = {{0}}, p_k = 0, gp_k[3] = {0}, lap_k[3] = {0};
+        for (int k = 0; k < K; ++k) {
+          const double sk = sol_old[dofs[k]], so = sol_old_old[dofs[k]];
+          const int a = T.node[k], c = T.comp[k];
+          if (c < dim) {
+            u_k[c] += sk * phi_u[k][c];
+            u_o[c] += so * phi_u[k][c];
+            for (int m = 0; m < dim; ++m) { gu_k[c][m] += sk * grad_phi_u[k][c][m]; gu_o[c][m] += so * grad_phi_u[k][c][m]; }
+            /* laplacian of the P2 node function: 4 |g_i|^2 (vertex), 8 g_i.g_j (line) */
+            const int i = T.idx[a][0], j = T.idx[a][1];
+            double gg = 0;
+            for (int m = 0; m < dim; ++m) gg += gl[i][m] * gl[j][m];
+            lap_k[c] += sk * (a < NV ? 4.0 : 8.0) * gg;
+          } else {
+            p_k += sk * phi_p[k];
+            for (int m = 0; m < dim; ++m) gp_k[m] += sk * grad_phi_p[k][m];
+          }
+        }
+        double conv_k[3] = {0}, conv_o[3] = {0}, tr = 0, um = 0;
+        for (int c = 0; c < dim; ++c) {
+          for (int m = 0; m < dim; ++m) { conv_k[c] += gu_k[c][m] * u_k[m]; conv_o[c] += gu_o[c][m] * u_o[m]; }
+          tr += gu_k[c][c];
+          um += u_k[c] * u_k[c];
+        }
+        um = sqrt(um);
+        const double tau = use_supg ? 1.0 / sqrt(pow(2.0 / deltat, 2) + pow(2.0 * um / h, 2) + pow(4.0 * nu / (h * h), 2)) : 0.0;
+        double Gu[34][3], gukphi[34][3];
+        for (int k = 0; k < K; ++k)
+          for (int c = 0; c < dim; ++c) {
+            double s1 = 0, s2 = 0;
+            for (int m = 0; m < dim; ++m) { s1 += grad_phi_u[k][c][m] * u_k[m]; s2 += gu_k[c][m] * phi_u[k][m]; }
+            Gu[k][c] = s1; gukphi[k][c] = s2;
+          }
+        for (int i = 0; i < K; ++i) {
+          /* minus the residual (cpp:377-418) */
+          double time_term = 0, conv_impl = 0, visc_impl = 0, conv_expl = 0, visc_expl = 0;
+          for (int c = 0; c < dim; ++c) {
+            time_term += (u_k[c] - u_o[c]) * phi_u[i][c] / deltat;
+            conv_impl += theta * conv_k[c] * phi_u[i][c];
+            conv_expl += (1.0 - theta) * conv_o[c] * phi_u[i][c];
+            for (int m = 0; m < dim; ++m) {
+              visc_impl += theta * nu * gu_k[c][m] * grad_phi_u[i][c][m];
+              visc_expl += (1.0 - theta) * nu * gu_o[c][m] * grad_phi_u[i][c][m];
+            }
+          }
+          const double pres_term = -p_k * div_phi_u[i], div_term = -phi_p[i] * tr;
+          cr[i] += (-time_term - conv_impl - visc_impl - conv_expl - visc_expl - pres_term - div_term) * JxW;
+          if (use_supg) {
+            double s = 0;                                   /* cpp:488-509 */
+            for (int c = 0; c < dim; ++c)
+              s += Gu[i][c] * ((u_k[c] - u_o[c]) / deltat + conv_k[c] + gp_k[c] - nu * lap_k[c]);
+            cr[i] -= s * tau * JxW;
+          }
+          /* Jacobian (cpp:421-466) */
+          for (int j = 0; j < K; ++j) {
+            double val = 0, visc = 0, cv = 0;
+            for (int c = 0; c < dim; ++c) {
+              val += phi_u[i][c] * phi_u[j][c] / deltat;
+              for (int m = 0; m < dim; ++m) visc += grad_phi_u[i][c][m] * grad_phi_u[j][c][m];
+              cv += (Gu[j][c] + gukphi[j][c]) * phi_u[i][c];
+            }
+            val += theta * nu * visc + theta * cv;
+            val -= phi_p[j] * div_phi_u[i];
+            val -= phi_p[i] * div_phi_u[j];
+            cm[i][j] += val * JxW;
+            if (use_supg) {
+              double s = 0;
+              for (int c = 0; c < dim; ++c)
+                s += tau * Gu[i][c] * (phi_u[j][c] / deltat + Gu[j][c] + gukphi[j][c] + grad_phi_p[j][c]);
+              cm[i][j] += s * JxW;
+              cm[i][j] += gamma * (div_phi_u[i] * div_phi_u[j]) * JxW;
+            }
+            if (Mp) cmp_[i][j] += phi_p[i] * phi_p[j] * JxW;
+            if (Kp) {
+              double g = 0;
+              for (int m = 0; m < dim; ++m) g += grad_phi_p[i][m] * grad_phi_p[j][m];
+              ckp[i][j] += g * JxW;
+            }
+          }
+        }
+        continue;
       }
       /* get_function_values / gradients (cpp:653-658) */
       double u_old[3] = {0}, u_oo[3] = {0}, gu_old[3][3] = {{0}};
@@ -281,6 +368,23 @@ void nso_assemble_linearized(int dim, int64_t n_cells, const double *points, con
   }
   if (Kp && Mp)
     for (int64_t k = 0; k < rowptr[N]; ++k) Kp[k] += 1e-6 * Mp[k];     /* cpp:536, 828 */
+}
+
+void nso_assemble_linearized(int dim, int64_t n_cells, const double *points, const int32_t *cells, const int32_t *cell_dofs,
+                             int64_t N, const int64_t *rowptr, const int32_t *col, const unsigned char *is_c,
+                             const double *cval, const double *sol_old, const double *sol_old_old, double deltat,
+                             double theta, double nu, int use_supg, double gamma, int first_order_ustar, double *A,
+                             double *b, double *Mp, double *Kp) {
+  assemble_impl(0, dim, n_cells, points, cells, cell_dofs, N, rowptr, col, is_c, cval, sol_old, sol_old_old, deltat, theta, nu,
+                use_supg, gamma, first_order_ustar, A, b, Mp, Kp);
+}
+
+void nso_assemble_newton(int dim, int64_t n_cells, const double *points, const int32_t *cells, const int32_t *cell_dofs,
+                         int64_t N, const int64_t *rowptr, const int32_t *col, const unsigned char *is_c, const double *cval,
+                         const double *sol_current, const double *sol_old, double deltat, double theta, double nu, int use_supg,
+                         double gamma, double *A, double *b, double *Mp, double *Kp) {
+  assemble_impl(1, dim, n_cells, points, cells, cell_dofs, N, rowptr, col, is_c, cval, sol_current, sol_old, deltat, theta, nu,
+                use_supg, gamma, 1, A, b, Mp, Kp);
 }
 
 /* ------------------------------------------------------------------ ILU(k) over row blocks */

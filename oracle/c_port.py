@@ -66,6 +66,29 @@ def assemble_linearized_raw(dim, points, cells, cell_dofs, N, pattern, is_c, cva
     return A, b, Mp, Kp
 
 
+def assemble_newton(mesh, dm, pattern, p, con, sol_current, sol_old, with_pressure_matrices=True):
+    """Same contract as oracle.assemble.assemble(kind='newton'); returns (A, b, Mp, Kp)."""
+    rowptr, col = pattern
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    N, nnz = dm.n_dofs, col.shape[0]
+    A, b = np.empty(nnz), np.empty(N)
+    Mp = np.empty(nnz) if with_pressure_matrices else None
+    Kp = np.empty(nnz) if with_pressure_matrices else None
+    is_c = np.ascontiguousarray(con.is_c, dtype=np.uint8)
+    cval = np.ascontiguousarray(con.val, dtype=np.float64)
+    pts = np.ascontiguousarray(mesh.points[:, :mesh.dim], dtype=np.float64)
+    cells = np.ascontiguousarray(mesh.cells, dtype=np.int32)
+    cdofs = np.ascontiguousarray(dm.cell_dofs, dtype=np.int32)
+    sc = np.ascontiguousarray(sol_current, dtype=np.float64)
+    so = np.ascontiguousarray(sol_old, dtype=np.float64)
+    lib().nso_assemble_newton(
+        ctypes.c_int(mesh.dim), ctypes.c_int64(cells.shape[0]), _p(pts), _p(cells), _p(cdofs), ctypes.c_int64(N),
+        _p(rowptr), _p(col), _p(is_c), _p(cval), _p(sc), _p(so), ctypes.c_double(p.dt), ctypes.c_double(p.theta),
+        ctypes.c_double(p.nu), ctypes.c_int(int(p.use_supg)), ctypes.c_double(p.gamma), _p(A), _p(b), _p(Mp), _p(Kp))
+    return A, b, Mp, Kp
+
+
 def assemble_linearized(mesh, dm, pattern, p, con, sol_old, sol_old_old, with_pressure_matrices=True):
     """Same contract as oracle.assemble.assemble(kind='linearized'); returns (A, b, Mp, Kp)."""
     return assemble_linearized_raw(mesh.dim, mesh.points, mesh.cells, dm.cell_dofs, dm.n_dofs, pattern, con.is_c, con.val,

@@ -35,6 +35,21 @@ def test_c_assembly_matches_numpy_oracle_2d(golden_mesh, supg, first_step):
     assert _rel(Mp, ref.Mp) < 1e-13 and _rel(Kp, ref.Kp) < 1e-13
 
 
+@pytest.mark.parametrize("supg", [False, True])
+def test_c_newton_assembly_matches_numpy_oracle_2d(golden_mesh, supg):
+    mesh = golden_mesh("mesh-2D")
+    dm = odofs.enumerate_dofs(mesh)
+    pat = odofs.make_sparsity(dm)
+    con = odofs.build_constraints(mesh, dm, None, pp.boundary_ids(2), homogeneous=True)
+    uk, un = synthetic_state(dm, 2, 1.0)
+    uk[dm.n_u:] = np.random.default_rng(3).standard_normal(dm.n_p)
+    p = asm.Params(dt=0.05, theta=1.0, nu=1e-3, use_supg=supg)
+    ref = asm.assemble(mesh, dm, pat, p, con, "newton", uk, un)
+    A, b, Mp, Kp = c_port.assemble_newton(mesh, dm, pat, p, con, uk, un)
+    assert _rel(A, ref.A) < 1e-13 and _rel(b, ref.b) < 1e-13
+    assert _rel(Mp, ref.Mp) < 1e-13 and _rel(Kp, ref.Kp) < 1e-13
+
+
 def test_fast_sparsity_equals_reference_construction(golden_mesh, small_3d_mesh):
     for mesh in (golden_mesh("mesh-2D"), small_3d_mesh):
         dm = odofs.enumerate_dofs(mesh)
@@ -49,6 +64,13 @@ def test_c_assembly_and_solve_3d(small_3d_mesh):
     A, b, Mp, Kp = c_port.assemble_linearized(mesh, dm, pat, p, con, un, unm1)
     assert _rel(A, ref.A) < 1e-13 and _rel(b, ref.b) < 1e-13
     N = dm.n_dofs
+    # Newton system with SUPG + grad-div in 3-D (cpp:278-539)
+    uk = un.copy()
+    uk[dm.n_u:] = np.random.default_rng(3).standard_normal(dm.n_p)
+    conh = odofs.build_constraints(mesh, dm, None, pp.boundary_ids(3), homogeneous=True)
+    refn = asm.assemble(mesh, dm, pat, p, conh, "newton", uk, unm1)
+    An, bn, _, _ = c_port.assemble_newton(mesh, dm, pat, p, conh, uk, unm1)
+    assert _rel(An, refn.A) < 1e-13 and _rel(bn, refn.b) < 1e-13
     x, its, res, ok = c_port.solve(pat, N, dm.n_u, A, Mp, Kp, b, p, nblocks=4)
     assert ok and 0 < its < 200
     Ac = asm.to_csr(pat, A, N)
