@@ -348,6 +348,11 @@ def main():
             ach = bytes_alg[dom] / (kernels[dom]["ms_avg"] * 1e-3) / 1e9
             line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                 "traffic": recorded_traffic(args.level, dom + ("_ebe" if dom == "spmv_vel" and opts_eff["precond_operator"] == 2 else "")) if world == 1 else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_alg[dom])}
+            tr = line["roofline"]["traffic"]
+            if tr:
+                # what the kernel really moves (compressed indices, fp32 operator copy) against the same peak
+                line["roofline"]["dram_GBps"] = tr / (kernels[dom]["ms_avg"] * 1e-3) / 1e9
+                line["roofline"]["dram_frac"] = line["roofline"]["dram_GBps"] / peak
         for k in ("spmv", "asm_rows"):
             if k in kernels:
                 kernels[k]["algorithmic_GBps"] = round(bytes_alg[k] / (kernels[k]["ms_avg"] * 1e-3) / 1e9, 1)
