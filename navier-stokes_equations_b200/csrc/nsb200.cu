@@ -909,109 +909,36 @@ void build_tiles(nsb_ctx* c) {
   c->n_tiles = (int)tp.size() - 1;
   c->tile_smem_bytes = budget * 8;
   c->d_tile_ptr.upload(tp, c->stream);
-  // SpMV tiles: consecutive nodes with bounded staged index count and bounded UNIQUE neighbour sets
+  // SpMV tiles (plan built and checked on the host: structure.cpp build_tile_plan / verify_tile_plan)
   {
-    const int ntot = S.nn_own + S.nn_ghost, ptot = S.np_own + S.np_ghost;
-    std::vector<int> sp, uptr, uxoff, pptr, pxoff, tiles_int, tiles_bnd;
-    std::vector<unsigned short> nloc(S.nbr.size()), ploc(S.pnbr.size());
-    std::vector<int> stamp(ntot, -1), pstamp(ptot, -1), posn(ntot, 0), posp(ptot, 0);
-    sp.push_back(0); uptr.push_back(0); pptr.push_back(0);
-    int A = 0, tile = 0;
-    std::vector<int> U, PU;
-    while (A < S.nn_own) {
-      U.clear(); PU.clear();
-      int idx = 0, cn = 0;
-      const int start = A;
-      while (A < S.nn_own && cn < TILE_MAX_NODES) {
-        const int nb = (int)(S.nbr_ptr[A + 1] - S.nbr_ptr[A]), np = (int)(S.pnbr_ptr[A + 1] - S.pnbr_ptr[A]);
-        if (nb + np > TILE_MAX_IDX || nb > TILE_MAX_UNIQ || np > TILE_MAX_PUNIQ)
-          throw CudaErr{"a node has more neighbours than one SpMV tile can stage"};
-        if (idx + nb + np > TILE_MAX_IDX) break;
-        int newu = 0, newp = 0;
-        for (int64_t k = S.nbr_ptr[A]; k < S.nbr_ptr[A + 1]; ++k) newu += stamp[S.nbr[k]] != tile;
-        for (int64_t k = S.pnbr_ptr[A]; k < S.pnbr_ptr[A + 1]; ++k) newp += pstamp[S.pnbr[k]] != tile;
-        if ((int)U.size() + newu > TILE_MAX_UNIQ || (int)PU.size() + newp > TILE_MAX_PUNIQ) break;
-        for (int64_t k = S.nbr_ptr[A]; k < S.nbr_ptr[A + 1]; ++k)
-          if (stamp[S.nbr[k]] != tile) { stamp[S.nbr[k]] = tile; U.push_back(S.nbr[k]); }
-        for (int64_t k = S.pnbr_ptr[A]; k < S.pnbr_ptr[A + 1]; ++k)
-          if (pstamp[S.pnbr[k]] != tile) { pstamp[S.pnbr[k]] = tile; PU.push_back(S.pnbr[k]); }
-        idx += nb + np; ++cn; ++A;
-      }
-      // memory order, then positions
-      std::sort(U.begin(), U.end(), [&](int a, int b) { return S.node_xoff(a) < S.node_xoff(b); });
-      std::sort(PU.begin(), PU.end(), [&](int a, int b) { return S.pid_xoff(a) < S.pid_xoff(b); });
-      for (size_t i = 0; i < U.size(); ++i) { posn[U[i]] = (int)i; uxoff.push_back((int)S.node_xoff(U[i])); }
-      for (size_t i = 0; i < PU.size(); ++i) { posp[PU[i]] = (int)i; pxoff.push_back((int)S.pid_xoff(PU[i])); }
-      for (int B = start; B < A; ++B) {
-        for (int64_t k = S.nbr_ptr[B]; k < S.nbr_ptr[B + 1]; ++k) nloc[k] = (unsigned short)posn[S.nbr[k]];
-        for (int64_t k = S.pnbr_ptr[B]; k < S.pnbr_ptr[B + 1]; ++k) ploc[k] = (unsigned short)posp[S.pnbr[k]];
-      }
-      bool reads_ghost = false;
-      for (int n : U) reads_ghost |= (n >= S.nn_own);
-      (reads_ghost ? tiles_bnd : tiles_int).push_back(tile);
-      sp.push_back(A); uptr.push_back((int)uxoff.size()); pptr.push_back((int)pxoff.size());
-      ++tile;
+    TilePlan P;
+    const TileLimits L{TILE_MAX_NODES, TILE_MAX_IDX, TILE_MAX_UNIQ, TILE_MAX_PUNIQ};
+    const std::string err = build_tile_plan(S, L, c->opt.precond_operator == 2, P);
+    if (!err.empty()) throw CudaErr{err};
+    c->n_stiles = P.n_tiles();
+    c->ebe_ypair_doubles = P.max_pairs * S.dim;
+    c->ebe_smem_bytes = 0;
+    if (c->opt.precond_operator == 2) {
+      c->ebe_smem_bytes = (c->ebe_ypair_doubles + P.max_ucells * ((S.dim + 1) * S.dim + 1)) * (int)sizeof(double);
+      c->d_pair_loc.upload(P.pair_loc, c->stream);
+      c->d_pair_ca.upload(P.pair_ca, c->stream);
+      c->d_tile_cell_ptr.upload(P.tile_cell_ptr, c->stream);
+      c->d_tile_cells.upload(P.tile_cells, c->stream);
+      c->s_rows.alloc(P.pair_loc.size());
+      CK(cudaMemsetAsync(c->s_rows.p, 0, P.pair_loc.size() * sizeof(float), c->stream));
+    } else {
+      c->d_pair_loc.alloc(0); c->d_pair_ca.alloc(0);
+      c->d_tile_cell_ptr.alloc(0); c->d_tile_cells.alloc(0);
+      c->s_rows.alloc(0);
     }
-    c->n_stiles = (int)sp.size() - 1;
-    // element-wise velocity operator: tile-local position of every cell node of every (node, cell) pair,
-    // blocked by 32 pairs like the S rows the assembly writes (ebe.cuh); shared memory for the pair results
-    {
-      const int NN = S.NN;
-      const int64_t NP = (int64_t)S.n2c.size();
-      int max_pairs = 0;
-      for (size_t t = 0; t + 1 < sp.size(); ++t)
-        max_pairs = std::max(max_pairs, (int)(S.n2c_ptr[sp[t + 1]] - S.n2c_ptr[sp[t]]));
-      c->ebe_ypair_doubles = max_pairs * S.dim;
-      c->ebe_smem_bytes = 0;
-      if (c->opt.precond_operator == 2) {
-        std::vector<unsigned short> pl((size_t)((NP + 31) / 32) * 32 * NN, 0), pca((size_t)NP, 0);
-#pragma omp parallel for schedule(static)
-        for (int B = 0; B < S.nn_own; ++B)
-          for (int64_t k = S.n2c_ptr[B]; k < S.n2c_ptr[B + 1]; ++k) {
-            const uint32_t pk = S.n2c[k];
-            const size_t cell = pk >> 4, a = pk & 15u;
-            for (int b = 0; b < NN; ++b) {
-              const int rk = S.rank_uu[(cell * NN + a) * NN + b];
-              pl[((size_t)(k >> 5) * (NN / 2) + (size_t)(b >> 1)) * 64 + (size_t)(k & 31) * 2 + (size_t)(b & 1)] = nloc[S.nbr_ptr[B] + rk];
-            }
-          }
-        // unique cells per tile (ascending) and the pair's position in that list
-        std::vector<int> tcp(1, 0), tcells, cpos(S.nc, 0), uc;
-        int max_ucells = 0;
-        for (size_t t = 0; t + 1 < sp.size(); ++t) {
-          uc.clear();
-          for (int64_t k = S.n2c_ptr[sp[t]]; k < S.n2c_ptr[sp[t + 1]]; ++k) uc.push_back((int)(S.n2c[k] >> 4));
-          std::sort(uc.begin(), uc.end());
-          uc.erase(std::unique(uc.begin(), uc.end()), uc.end());
-          if (uc.size() > 4096) throw CudaErr{"an SpMV tile touches more than 4096 cells"};
-          for (size_t i = 0; i < uc.size(); ++i) cpos[uc[i]] = (int)i;
-          for (int64_t k = S.n2c_ptr[sp[t]]; k < S.n2c_ptr[sp[t + 1]]; ++k)
-            pca[k] = (unsigned short)((cpos[S.n2c[k] >> 4] << 4) | (S.n2c[k] & 15u));
-          tcells.insert(tcells.end(), uc.begin(), uc.end());
-          tcp.push_back((int)tcells.size());
-          max_ucells = std::max(max_ucells, (int)uc.size());
-        }
-        c->ebe_smem_bytes = (c->ebe_ypair_doubles + max_ucells * ((S.dim + 1) * S.dim + 1)) * (int)sizeof(double);
-        c->d_pair_loc.upload(pl, c->stream);
-        c->d_pair_ca.upload(pca, c->stream);
-        c->d_tile_cell_ptr.upload(tcp, c->stream);
-        c->d_tile_cells.upload(tcells, c->stream);
-        c->s_rows.alloc(pl.size());
-        CK(cudaMemsetAsync(c->s_rows.p, 0, pl.size() * sizeof(float), c->stream));
-      } else {
-        c->d_pair_loc.alloc(0); c->d_pair_ca.alloc(0);
-        c->d_tile_cell_ptr.alloc(0); c->d_tile_cells.alloc(0);
-        c->s_rows.alloc(0);
-      }
-      c->ebe_valid = false;
-    }
-    c->d_stile_ptr.upload(sp, c->stream);
-    c->n_tiles_int = (int)tiles_int.size(); c->n_tiles_bnd = (int)tiles_bnd.size();
-    c->d_tiles_int.upload(tiles_int, c->stream); c->d_tiles_bnd.upload(tiles_bnd, c->stream);
-    c->d_suniq_ptr.upload(uptr, c->stream); c->d_suniq_xoff.upload(uxoff, c->stream);
-    c->d_spuniq_ptr.upload(pptr, c->stream); c->d_spuniq_xoff.upload(pxoff, c->stream);
-    c->d_nbr_loc.upload(nloc, c->stream); c->d_pnbr_loc.upload(ploc, c->stream);
-    CK(cudaStreamSynchronize(c->stream));
+    c->ebe_valid = false;
+    c->d_stile_ptr.upload(P.node_ptr, c->stream);
+    c->n_tiles_int = (int)P.tiles_int.size(); c->n_tiles_bnd = (int)P.tiles_bnd.size();
+    c->d_tiles_int.upload(P.tiles_int, c->stream); c->d_tiles_bnd.upload(P.tiles_bnd, c->stream);
+    c->d_suniq_ptr.upload(P.uniq_ptr, c->stream); c->d_suniq_xoff.upload(P.uniq_xoff, c->stream);
+    c->d_spuniq_ptr.upload(P.puniq_ptr, c->stream); c->d_spuniq_xoff.upload(P.puniq_xoff, c->stream);
+    c->d_nbr_loc.upload(P.nbr_loc, c->stream); c->d_pnbr_loc.upload(P.pnbr_loc, c->stream);
+    CK(cudaStreamSynchronize(c->stream));       // the plan's host vectors die with this scope
     c->stiles.node_ptr = c->d_stile_ptr.p;
     c->stiles.uniq_ptr = c->d_suniq_ptr.p; c->stiles.uniq_xoff = c->d_suniq_xoff.p;
     c->stiles.puniq_ptr = c->d_spuniq_ptr.p; c->stiles.puniq_xoff = c->d_spuniq_xoff.p;
@@ -1799,6 +1726,24 @@ int nsb_test_halo_plan(int dim, int64_t n_vertices, const double* coords, int64_
 }
 
 /* eigenvalues of an upper-Hessenberg matrix */
+// host-only: builds rank's structure and SpMV tile plan (optionally with the element-wise arrays) and checks every
+// invariant the kernels rely on; out = {tiles, interior tiles, boundary tiles, max pairs per tile, violations}
+int nsb_test_tile_plan(int dim, int64_t n_vertices, const double* coords, int64_t n_cells, const uint32_t* cell_vertices,
+                       const uint32_t* cell_dofs, int64_t n_u, int64_t n_p, const int32_t* cell_part, int rank, int nranks,
+                       int with_elementwise, int64_t* out5) {
+  Structure S;
+  const std::string e = build_structure(dim, n_vertices, coords, n_cells, cell_vertices, cell_dofs, n_u, n_p,
+                                        nranks > 1 ? cell_part : nullptr, rank, nranks, S);
+  if (!e.empty()) { std::fprintf(stderr, "nsb_test_tile_plan: %s\n", e.c_str()); return -1; }
+  TilePlan P;
+  const TileLimits L{TILE_MAX_NODES, TILE_MAX_IDX, TILE_MAX_UNIQ, TILE_MAX_PUNIQ};
+  const std::string e2 = build_tile_plan(S, L, with_elementwise != 0, P);
+  if (!e2.empty()) { std::fprintf(stderr, "nsb_test_tile_plan: %s\n", e2.c_str()); return -1; }
+  out5[0] = P.n_tiles(); out5[1] = (int64_t)P.tiles_int.size(); out5[2] = (int64_t)P.tiles_bnd.size();
+  out5[3] = P.max_pairs; out5[4] = verify_tile_plan(S, L, P);
+  return 0;
+}
+
 int nsb_test_hessenberg_eigs(int n, const double* a, double* wr, double* wi) {
   std::vector<double> A(a, a + (size_t)n * n), r, i;
   if (!hessenberg_eigs(n, A, r, i)) return 1;

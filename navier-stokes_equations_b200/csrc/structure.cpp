@@ -394,4 +394,141 @@ void export_row_gids(const Structure& S, std::vector<int64_t>& gid) {
   for (int P = 0; P < S.np_own; ++P) gid[(int64_t)S.dim * S.nn_own + P] = S.n_u_glob + S.pid_gid[P];
 }
 
+std::string build_tile_plan(const Structure& S, const TileLimits& L, bool with_elementwise, TilePlan& P) {
+  P = TilePlan();
+  const int ntot = S.nn_own + S.nn_ghost, ptot = S.np_own + S.np_ghost;
+  P.nbr_loc.assign(S.nbr.size(), 0);
+  P.pnbr_loc.assign(S.pnbr.size(), 0);
+  std::vector<int> stamp(ntot, -1), pstamp(ptot, -1), posn(ntot, 0), posp(ptot, 0);
+  P.node_ptr.push_back(0); P.uniq_ptr.push_back(0); P.puniq_ptr.push_back(0);
+  int A = 0, tile = 0;
+  std::vector<int> U, PU;
+  while (A < S.nn_own) {
+    U.clear(); PU.clear();
+    int idx = 0, cn = 0;
+    const int start = A;
+    while (A < S.nn_own && cn < L.max_nodes) {
+      const int nb = (int)(S.nbr_ptr[A + 1] - S.nbr_ptr[A]), np = (int)(S.pnbr_ptr[A + 1] - S.pnbr_ptr[A]);
+      if (nb + np > L.max_idx || nb > L.max_uniq || np > L.max_puniq)
+        return "a node has more neighbours than one SpMV tile can stage";
+      if (idx + nb + np > L.max_idx) break;
+      int newu = 0, newp = 0;
+      for (int64_t k = S.nbr_ptr[A]; k < S.nbr_ptr[A + 1]; ++k) newu += stamp[S.nbr[k]] != tile;
+      for (int64_t k = S.pnbr_ptr[A]; k < S.pnbr_ptr[A + 1]; ++k) newp += pstamp[S.pnbr[k]] != tile;
+      if ((int)U.size() + newu > L.max_uniq || (int)PU.size() + newp > L.max_puniq) break;
+      for (int64_t k = S.nbr_ptr[A]; k < S.nbr_ptr[A + 1]; ++k)
+        if (stamp[S.nbr[k]] != tile) { stamp[S.nbr[k]] = tile; U.push_back(S.nbr[k]); }
+      for (int64_t k = S.pnbr_ptr[A]; k < S.pnbr_ptr[A + 1]; ++k)
+        if (pstamp[S.pnbr[k]] != tile) { pstamp[S.pnbr[k]] = tile; PU.push_back(S.pnbr[k]); }
+      idx += nb + np; ++cn; ++A;
+    }
+    // memory order, then positions
+    std::sort(U.begin(), U.end(), [&](int a, int b) { return S.node_xoff(a) < S.node_xoff(b); });
+    std::sort(PU.begin(), PU.end(), [&](int a, int b) { return S.pid_xoff(a) < S.pid_xoff(b); });
+    for (size_t i = 0; i < U.size(); ++i) { posn[U[i]] = (int)i; P.uniq_xoff.push_back((int)S.node_xoff(U[i])); }
+    for (size_t i = 0; i < PU.size(); ++i) { posp[PU[i]] = (int)i; P.puniq_xoff.push_back((int)S.pid_xoff(PU[i])); }
+    for (int B = start; B < A; ++B) {
+      for (int64_t k = S.nbr_ptr[B]; k < S.nbr_ptr[B + 1]; ++k) P.nbr_loc[k] = (unsigned short)posn[S.nbr[k]];
+      for (int64_t k = S.pnbr_ptr[B]; k < S.pnbr_ptr[B + 1]; ++k) P.pnbr_loc[k] = (unsigned short)posp[S.pnbr[k]];
+    }
+    bool reads_ghost = false;
+    for (int n : U) reads_ghost |= (n >= S.nn_own);
+    (reads_ghost ? P.tiles_bnd : P.tiles_int).push_back(tile);
+    P.node_ptr.push_back(A); P.uniq_ptr.push_back((int)P.uniq_xoff.size()); P.puniq_ptr.push_back((int)P.puniq_xoff.size());
+    ++tile;
+  }
+  const auto& sp = P.node_ptr;
+  for (size_t t = 0; t + 1 < sp.size(); ++t)
+    P.max_pairs = std::max(P.max_pairs, (int)(S.n2c_ptr[sp[t + 1]] - S.n2c_ptr[sp[t]]));
+  if (!with_elementwise) return "";
+  // element-wise velocity operator: tile-local position of every cell node of every (node, cell) pair, blocked by
+  // 32 pairs like the S rows the assembly writes (ebe.cuh)
+  const int NN = S.NN;
+  const int64_t NP = (int64_t)S.n2c.size();
+  P.pair_loc.assign((size_t)((NP + 31) / 32) * 32 * NN, 0);
+  P.pair_ca.assign((size_t)NP, 0);
+#pragma omp parallel for schedule(static)
+  for (int B = 0; B < S.nn_own; ++B)
+    for (int64_t k = S.n2c_ptr[B]; k < S.n2c_ptr[B + 1]; ++k) {
+      const uint32_t pk = S.n2c[k];
+      const size_t cell = pk >> 4, a = pk & 15u;
+      for (int b = 0; b < NN; ++b) {
+        const int rk = S.rank_uu[(cell * NN + a) * NN + b];
+        P.pair_loc[ebe_pair_index(NN, k, b)] = P.nbr_loc[S.nbr_ptr[B] + rk];
+      }
+    }
+  // unique cells per tile (ascending) and the pair's position in that list
+  std::vector<int> cpos(S.nc, 0), uc;
+  P.tile_cell_ptr.assign(1, 0);
+  for (size_t t = 0; t + 1 < sp.size(); ++t) {
+    uc.clear();
+    for (int64_t k = S.n2c_ptr[sp[t]]; k < S.n2c_ptr[sp[t + 1]]; ++k) uc.push_back((int)(S.n2c[k] >> 4));
+    std::sort(uc.begin(), uc.end());
+    uc.erase(std::unique(uc.begin(), uc.end()), uc.end());
+    if (uc.size() > 4096) return "an SpMV tile touches more than 4096 cells";
+    for (size_t i = 0; i < uc.size(); ++i) cpos[uc[i]] = (int)i;
+    for (int64_t k = S.n2c_ptr[sp[t]]; k < S.n2c_ptr[sp[t + 1]]; ++k)
+      P.pair_ca[k] = (unsigned short)((cpos[S.n2c[k] >> 4] << 4) | (S.n2c[k] & 15u));
+    P.tile_cells.insert(P.tile_cells.end(), uc.begin(), uc.end());
+    P.tile_cell_ptr.push_back((int)P.tile_cells.size());
+    P.max_ucells = std::max(P.max_ucells, (int)uc.size());
+  }
+  return "";
+}
+
+int64_t verify_tile_plan(const Structure& S, const TileLimits& L, const TilePlan& P) {
+  int64_t bad = 0;
+  const int nt = P.n_tiles();
+  if (nt < 0 || P.node_ptr.empty() || P.node_ptr.front() != 0 || P.node_ptr.back() != S.nn_own) return 1;
+  if ((int)P.uniq_ptr.size() != nt + 1 || (int)P.puniq_ptr.size() != nt + 1) return 1;
+  std::vector<char> seen(nt, 0);
+  for (int t : P.tiles_int) { if (t < 0 || t >= nt || seen[t]) ++bad; else seen[t] = 1; }
+  for (int t : P.tiles_bnd) { if (t < 0 || t >= nt || seen[t]) ++bad; else seen[t] = 2; }
+  for (int t = 0; t < nt; ++t) if (!seen[t]) ++bad;
+  if (bad) return bad;
+  const bool ebe = !P.tile_cell_ptr.empty();
+  for (int t = 0; t < nt; ++t) {
+    const int n0 = P.node_ptr[t], n1 = P.node_ptr[t + 1];
+    const int u0 = P.uniq_ptr[t], nu = P.uniq_ptr[t + 1] - u0, q0 = P.puniq_ptr[t], nq = P.puniq_ptr[t + 1] - q0;
+    if (n1 <= n0 || n1 - n0 > L.max_nodes || nu > L.max_uniq || nq > L.max_puniq) ++bad;
+    int64_t idx = 0;
+    bool ghost = false;
+    for (int i = 1; i < nu; ++i) if (P.uniq_xoff[u0 + i] <= P.uniq_xoff[u0 + i - 1]) ++bad;      // memory order, unique
+    for (int i = 1; i < nq; ++i) if (P.puniq_xoff[q0 + i] <= P.puniq_xoff[q0 + i - 1]) ++bad;
+    for (int i = 0; i < nu; ++i) ghost |= P.uniq_xoff[u0 + i] >= S.n_own_dofs();
+    if ((seen[t] == 2) != ghost) ++bad;
+    for (int A = n0; A < n1; ++A) {
+      idx += (S.nbr_ptr[A + 1] - S.nbr_ptr[A]) + (S.pnbr_ptr[A + 1] - S.pnbr_ptr[A]);
+      for (int64_t k = S.nbr_ptr[A]; k < S.nbr_ptr[A + 1]; ++k) {
+        const int loc = P.nbr_loc[k];
+        if (loc >= nu || P.uniq_xoff[u0 + loc] != (int)S.node_xoff(S.nbr[k])) ++bad;
+      }
+      for (int64_t k = S.pnbr_ptr[A]; k < S.pnbr_ptr[A + 1]; ++k) {
+        const int loc = P.pnbr_loc[k];
+        if (loc >= nq || P.puniq_xoff[q0 + loc] != (int)S.pid_xoff(S.pnbr[k])) ++bad;
+      }
+    }
+    if (idx > L.max_idx) ++bad;
+    const int64_t p0 = S.n2c_ptr[n0], p1 = S.n2c_ptr[n1];
+    if (p1 - p0 > P.max_pairs) ++bad;
+    if (!ebe) continue;
+    const int c0 = P.tile_cell_ptr[t], nc = P.tile_cell_ptr[t + 1] - c0;
+    if (nc > P.max_ucells || nc > 4096) ++bad;
+    for (int i = 1; i < nc; ++i) if (P.tile_cells[c0 + i] <= P.tile_cells[c0 + i - 1]) ++bad;
+    for (int A = n0; A < n1; ++A)
+      for (int64_t k = S.n2c_ptr[A]; k < S.n2c_ptr[A + 1]; ++k) {
+        const int cell = (int)(S.n2c[k] >> 4), a = (int)(S.n2c[k] & 15u);
+        const int ca = P.pair_ca[k];
+        if ((ca & 15) != a || (ca >> 4) >= nc || P.tile_cells[c0 + (ca >> 4)] != cell) ++bad;
+        if (S.cell_nodes[(size_t)cell * S.NN + a] != A) ++bad;
+        for (int b = 0; b < S.NN; ++b) {
+          const int loc = P.pair_loc[ebe_pair_index(S.NN, k, b)];
+          const int node = S.cell_nodes[(size_t)cell * S.NN + b];
+          if (loc >= nu || P.uniq_xoff[u0 + loc] != (int)S.node_xoff(node)) ++bad;
+        }
+      }
+  }
+  return bad;
+}
+
 }  // namespace nsb

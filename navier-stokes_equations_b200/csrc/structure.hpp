@@ -73,6 +73,37 @@ std::string build_structure(int dim, int64_t n_vertices, const double* coords, i
                             const uint32_t* cell_vertices, const uint32_t* cell_dofs, int64_t n_u,
                             int64_t n_p, const int32_t* cell_part, int rank, int nranks, Structure& S);
 
+// Plan of the SpMV tiles (linalg.cuh / ebe.cuh): runs of consecutive owned nodes with bounded staged index count
+// and bounded UNIQUE neighbour sets; every neighbour reference rewritten as a 16-bit position in its tile's unique
+// list; tiles that read no ghost entry listed apart (halo / compute overlap); optionally the per-pair arrays of the
+// element-wise velocity operator.  Pure host logic, checked by verify_tile_plan() in the CPU tests.
+struct TileLimits {
+  int max_nodes, max_idx, max_uniq, max_puniq;
+};
+struct TilePlan {
+  std::vector<int> node_ptr;               // [n_tiles+1]
+  std::vector<int> uniq_ptr, uniq_xoff;    // unique neighbour nodes per tile (memory order), x offset of (node, 0)
+  std::vector<int> puniq_ptr, puniq_xoff;  // unique neighbour pressure DoFs per tile
+  std::vector<unsigned short> nbr_loc;     // parallel to Structure::nbr
+  std::vector<unsigned short> pnbr_loc;    // parallel to Structure::pnbr
+  std::vector<int> tiles_int, tiles_bnd;   // tiles without / with ghost neighbours
+  int max_pairs = 0;                       // most (node, cell) pairs in one tile
+  // element-wise operator (filled when requested)
+  std::vector<unsigned short> pair_loc;    // ebe_index(pair, b): position of cell node b in the tile's unique list
+  std::vector<unsigned short> pair_ca;     // [pairs] (position of the cell in the tile's cell list) << 4 | local node
+  std::vector<int> tile_cell_ptr, tile_cells;
+  int max_ucells = 0;
+  int n_tiles() const { return (int)node_ptr.size() - 1; }
+};
+// index of (pair p, cell node b) in the blocked pair arrays (two consecutive b per lane element, 32 pairs per row)
+inline size_t ebe_pair_index(int NN, int64_t p, int b) {
+  return ((size_t)(p >> 5) * (size_t)(NN / 2) + (size_t)(b >> 1)) * 64 + (size_t)(p & 31) * 2 + (size_t)(b & 1);
+}
+// Returns an empty string on success, else an error message.
+std::string build_tile_plan(const Structure& S, const TileLimits& L, bool with_elementwise, TilePlan& P);
+// Independent check of every invariant the kernels rely on; returns the number of violations (0 = consistent).
+int64_t verify_tile_plan(const Structure& S, const TileLimits& L, const TilePlan& P);
+
 // Expands the local rows to scalar CSR with GLOBAL column indices, rows in local owned
 // order (velocity rows then pressure rows); for the bit-exact pattern check.
 void export_pattern(const Structure& S, std::vector<int64_t>& rowptr, std::vector<uint32_t>& col);
