@@ -1,7 +1,9 @@
 """ORACLE (test infrastructure, not product code) -- cell-wise assembly.
 
 PARITY UNPINNED by the reference (it has no tests / golden vectors and cannot be built
-here: deal.II + Trilinos + MPI are absent).  This is a CPU restatement of
+here: deal.II + Trilinos + MPI are absent).  The one external known answer the oracle is held
+to is the published DFG benchmark 2D-1 (tests/test_oracle_pins.py::test_dfg_2d1_known_answer).
+This is a CPU restatement of
 
   NavierStokes<dim>::assemble_linearized_system()   reference src/classes/NavierStokes.cpp:569-831
   NavierStokes<dim>::assemble_newton_system()       reference src/classes/NavierStokes.cpp:278-539

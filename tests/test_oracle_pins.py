@@ -166,3 +166,18 @@ def test_elimination_rule():
     assert out[0, 2, 2] == (abs(M[0, 0, 0]) + abs(M[0, 1, 1]) + 0 + abs(M[0, 3, 3])) / 4   # average fallback
     assert rhs[0, 1] == 0 and rhs[0, 2] == 0
     assert rhs[0, 0] == r[0, 0] - M[0, 0, 1] * 10.0 - M[0, 0, 2] * (-1.0)
+
+
+def test_dfg_2d1_known_answer(golden_mesh):
+    """Known-answer pin from outside the repo: the reference's 2D-1 case is the DFG / Schaefer-Turek benchmark
+    "flow around a cylinder" 2D-1 (Re = 20, steady), whose published reference values are C_D = 5.5795,
+    C_L = 0.010619, Delta p = 0.11752.  The oracle -- the reference's assembly (cpp:278-539), boundary conditions
+    (cpp:229-253), Newton loop (cpp:1116-1207) and post-processing (cpp:871-1040) restated -- run on the shipped
+    mesh-2D.msh (1 606 P2/P1 triangles) reaches them to 0.3 % / 3 % / 0.1 %."""
+    from oracle import solve as osolve
+    o = osolve.Oracle(golden_mesh("mesh-2D"), "2D-1", solver="direct")
+    for _ in range(40):                      # dt = 0.1, inlet ramp until t = 1, steady by t = 4
+        info = o.step()
+    assert abs(info["cd"] - 5.5795) / 5.5795 < 0.01
+    assert abs(info["dp"] - 0.11752) / 0.11752 < 0.005
+    assert abs(info["cl"] - 0.010619) / 0.010619 < 0.10
