@@ -127,7 +127,10 @@ class Oracle:
     run() loop (cpp:1044-1327) with either the reference stopping rule (GMRES, 1e-2) or a
     direct solve (parity mode)."""
 
-    def __init__(self, mesh, case, solver="direct", deltat=None):
+    def __init__(self, mesh, case, solver="direct", deltat=None, c_assembly=False):
+        # c_assembly: assemble with the C/OpenMP port (oracle/c, equal to the numpy formulas to 1e-13, see
+        # tests/test_oracle_c.py) -- only to make long trajectories affordable; the parity tests keep numpy.
+        self.c_assembly = c_assembly
         tc = dict(pp.TEST_CASES[case]) if isinstance(case, str) else dict(case)
         self.tc = tc
         self.mesh = mesh
@@ -166,19 +169,32 @@ class Oracle:
 
     def assemble_linearized(self, p):
         con = odofs.build_constraints(self.mesh, self.dm, self.inlet(self.time), self.ids)
-        out = asm.assemble(self.mesh, self.dm, self.pattern, p, con, "linearized",
-                           self.solution_old, self.solution_old_old,
-                           with_pressure_matrices=self.Mp is None)
+        if self.c_assembly:
+            out = self._c_assemble("linearized", p, con, self.solution_old, self.solution_old_old)
+        else:
+            out = asm.assemble(self.mesh, self.dm, self.pattern, p, con, "linearized",
+                               self.solution_old, self.solution_old_old,
+                               with_pressure_matrices=self.Mp is None)
         if self.Mp is None:
             self.Mp, self.Kp = out.Mp, out.Kp
         return out, con
 
     def assemble_newton(self, p):
-        out = asm.assemble(self.mesh, self.dm, self.pattern, p, self.newton_constraints, "newton",
-                           self.current_solution, self.solution_old,
-                           with_pressure_matrices=self.Mp is None)
+        if self.c_assembly:
+            out = self._c_assemble("newton", p, self.newton_constraints, self.current_solution, self.solution_old)
+        else:
+            out = asm.assemble(self.mesh, self.dm, self.pattern, p, self.newton_constraints, "newton",
+                               self.current_solution, self.solution_old,
+                               with_pressure_matrices=self.Mp is None)
         if self.Mp is None:
             self.Mp, self.Kp = out.Mp, out.Kp
+        return out
+
+    def _c_assemble(self, kind, p, con, va, vb):
+        from . import c_port
+        f = c_port.assemble_newton if kind == "newton" else c_port.assemble_linearized
+        out = asm.Assembled()
+        out.A, out.b, out.Mp, out.Kp = f(self.mesh, self.dm, self.pattern, p, con, va, vb, with_pressure_matrices=True)
         return out
 
     def solve(self, out, con, p, max_it):

@@ -115,7 +115,7 @@ def test_poiseuille_patch(golden_mesh):
 
 
 def test_newton_converges_quadratically(golden_mesh):
-    o = osolve.Oracle(golden_mesh("mesh-2D"), "2D-1", solver="direct")
+    o = osolve.Oracle(golden_mesh("mesh-2D"), "2D-1", solver="direct", c_assembly=True)   # C port == numpy to 1e-13
     info = o.step()
     res = info["residuals"]
     assert info["newton_iters"] <= 4 and res[-1] < 1e-8
@@ -175,7 +175,7 @@ def test_dfg_2d1_known_answer(golden_mesh):
     (cpp:229-253), Newton loop (cpp:1116-1207) and post-processing (cpp:871-1040) restated -- run on the shipped
     mesh-2D.msh (1 606 P2/P1 triangles) reaches them to 0.3 % / 3 % / 0.1 %."""
     from oracle import solve as osolve
-    o = osolve.Oracle(golden_mesh("mesh-2D"), "2D-1", solver="direct")
+    o = osolve.Oracle(golden_mesh("mesh-2D"), "2D-1", solver="direct", c_assembly=True)   # C port == numpy to 1e-13
     for _ in range(40):                      # dt = 0.1, inlet ramp until t = 1, steady by t = 4
         info = o.step()
     assert abs(info["cd"] - 5.5795) / 5.5795 < 0.01
