@@ -123,3 +123,16 @@ def test_c_iluk_matches_dense_textbook(lof):
                                     ctypes.byref(nnz))
     assert nnz.value == nnz_ref
     assert _rel(y, y_ref) < 1e-12
+
+
+@pytest.mark.parametrize("case", ["2D-2", "2D-1"])
+def test_oracle_trajectory_same_with_c_assembly(golden_mesh, case):
+    """Oracle(c_assembly=True) -- used for the long known-answer runs -- follows the numpy oracle step by step."""
+    mesh = golden_mesh("mesh-2D")
+    a = osolve.Oracle(mesh, case, solver="direct")
+    b = osolve.Oracle(mesh, case, solver="direct", c_assembly=True)
+    for _ in range(3):
+        ia, ib = a.step(), b.step()
+        for k in ("cd", "cl", "dp"):
+            assert abs(ia[k] - ib[k]) <= 1e-9 * max(1.0, abs(ia[k]))
+    assert np.linalg.norm(a.current_solution - b.current_solution) <= 1e-10 * np.linalg.norm(a.current_solution)
