@@ -181,3 +181,25 @@ def test_dfg_2d1_known_answer(golden_mesh):
     assert abs(info["cd"] - 5.5795) / 5.5795 < 0.01
     assert abs(info["dp"] - 0.11752) / 0.11752 < 0.005
     assert abs(info["cl"] - 0.010619) / 0.010619 < 0.10
+
+
+def test_2d2_vortex_street_matches_reported_ranges(golden_mesh):
+    """SURVEY.md section 8c pin (7): the only 2D-2 output the reference publishes is its report's force plot,
+    C_D ~ 3.2 mean and C_L ~ +-1.5 (Navier_Stokes_equation.pdf p.13; the DFG benchmark has C_D max 3.22-3.24,
+    St 0.295-0.305).  The oracle's linearised Crank-Nicolson path on mesh-2D sheds vortices in those ranges
+    (mesh-2D-40 gives +-1.50 exactly, profiles/configs/dfg_known_answers.txt)."""
+    from oracle import solve as osolve
+    o = osolve.Oracle(golden_mesh("mesh-2D"), "2D-2", solver="direct", c_assembly=True)
+    assert o.deltat == 0.02                                   # compute_default_deltat(100), hpp:372
+    hist = []
+    while o.time < 6.0 - 1e-9:
+        info = o.step()
+        hist.append((info["time"], info["cd"], info["cl"]))
+    h = np.array(hist)
+    tail = h[h[:, 0] > 4.5]
+    cl, t = tail[:, 2], tail[:, 0]
+    up = t[1:][(cl[:-1] < 0) & (cl[1:] >= 0)]
+    strouhal = 0.1 / np.diff(up).mean()                       # D = 0.1, mean inlet velocity 1
+    assert 3.0 < tail[:, 1].mean() < 3.4
+    assert 1.0 < cl.max() < 1.6 and -1.6 < cl.min() < -1.0
+    assert 0.26 < strouhal < 0.31
