@@ -49,7 +49,7 @@ typedef struct nsb_solver_opts {
   int32_t amg_smoother_degree; /* Chebyshev sweeps per level, pre and post  (default 2)   */
   double schur_mass_coeff;  /* coefficient of M_p^-1; <0 = theta*nu + gamma_graddiv (default),
                                set to theta*nu for the reference's exact scaling (hpp:343) */
-  int32_t reorthogonalize;  /* 1 = classical Gram-Schmidt twice (default), 0 = once        */
+  int32_t reorthogonalize;  /* 0 or 1 = classical Gram-Schmidt twice (default), <0 = once  */
   int32_t precond_precision;/* storage of the operator used INSIDE the velocity polynomial: 32 (default; products are
                                accumulated in fp64, so the preconditioner stays a fixed linear operator) or 64.
                                Changing it invalidates the assembled system (re-assemble before solving). */

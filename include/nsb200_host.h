@@ -30,6 +30,8 @@ typedef struct nsh_options {
   int32_t max_steps;         /* run(): stop after this many steps; <0 = until T                  */
   const char* output_dir;    /* NULL = "./"                                                      */
   nsb_solver_opts solver;    /* zero = defaults                                                  */
+  int32_t test_fail_solves;  /* test hook: report the next k linear solves as not converged (drives the retry /
+                                fallback paths of run(), cpp:1174-1198, 1223-1286); 0 in production           */
 } nsh_options;
 
 typedef struct nsh_step_info {
@@ -49,6 +51,8 @@ int nsh_run(nsh_handle h);                               /* run()               
 int nsh_get_sizes(nsh_handle h, int64_t* n_u, int64_t* n_p, int64_t* n_cells, int64_t* n_vertices);
 int nsh_get_solution(nsh_handle h, double* current_solution /* [n_u+n_p] */);
 nsb_handle nsh_device(nsh_handle h);
+/* test hook, see nsh_options.test_fail_solves */
+int nsh_set_test_fail_solves(nsh_handle h, int32_t k);
 
 /* ---- host-only setup objects -------------------------------------------------------------- */
 int nshd_create(const char* mesh_file, int dim, nshd_handle* out);

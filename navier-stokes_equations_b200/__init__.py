@@ -4,7 +4,7 @@ Thin bindings only: the product is the CUDA/C++ behind the C ABI.  There is no C
 fallback -- loading fails loudly if the shared library is missing, and every call raises
 `NsbError` with the library's own message on a non-zero/negative return code.
 
-The directory name contains a '-', so import it by path (tests/conftest.py: `load_nsb()`).
+The directory name contains a '-', so it is imported by path: `import nsb200` (nsb200.py at the repository root).
 """
 from __future__ import annotations
 
@@ -142,7 +142,7 @@ class Device:
         self._ck(lib().nsb_set_params(self.h, C.byref(p)))
 
     def set_solver_opts(self, poly_degree_F=0, poly_refresh=0, poly_kind=0, poly_target=0.0, cheb_degree_Mp=0, amg_smoother_degree=0,
-                        schur_mass_coeff=0.0, reorthogonalize=1, precond_precision=0, precond_operator=0):
+                        schur_mass_coeff=0.0, reorthogonalize=0, precond_precision=0, precond_operator=0):
         o = NsbSolverOpts(poly_degree_F, poly_refresh, poly_kind, poly_target, cheb_degree_Mp, amg_smoother_degree, schur_mass_coeff, reorthogonalize, precond_precision,
                           precond_operator)
         self._ck(lib().nsb_set_solver_opts(self.h, C.byref(o)))
@@ -264,7 +264,7 @@ _hostlib = None
 class NshOptions(C.Structure):
     _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("nccl_unique_id", C.c_void_p),
                 ("write_vtu", C.c_int32), ("verbose", C.c_int32), ("gmres_tolerance", C.c_double), ("deltat", C.c_double),
-                ("max_steps", C.c_int32), ("output_dir", C.c_char_p), ("solver", NsbSolverOpts)]
+                ("max_steps", C.c_int32), ("output_dir", C.c_char_p), ("solver", NsbSolverOpts), ("test_fail_solves", C.c_int32)]
 
 
 class NshStepInfo(C.Structure):
@@ -300,12 +300,12 @@ class HostSolver:
     """NavierStokes<dim>(TestCases::make_<case>(mesh_file)) driven through the C facade."""
 
     def __init__(self, case, mesh_file, device=0, rank=0, nranks=1, nccl_unique_id=None, write_vtu=False, verbose=False,
-                 gmres_tolerance=0.0, deltat=0.0, output_dir=None, solver_opts=None):
+                 gmres_tolerance=0.0, deltat=0.0, output_dir=None, solver_opts=None, test_fail_solves=0):
         L = hostlib()
         self._uid = C.create_string_buffer(nccl_unique_id, 128) if nccl_unique_id else None
         self._outdir = output_dir.encode() if output_dir else None
         o = NshOptions(device, rank, nranks, C.cast(self._uid, C.c_void_p) if self._uid else None, int(write_vtu),
-                       int(verbose), gmres_tolerance, deltat, -1, self._outdir, solver_opts or NsbSolverOpts())
+                       int(verbose), gmres_tolerance, deltat, -1, self._outdir, solver_opts or NsbSolverOpts(), test_fail_solves)
         self.h = C.c_void_p()
         if L.nsh_create(case.encode(), mesh_file.encode(), C.byref(o), C.byref(self.h)) != 0:
             raise NsbError(L.nsh_last_error().decode())
@@ -325,6 +325,9 @@ class HostSolver:
         info = NshStepInfo()
         self._ck(hostlib().nsh_step(self.h, C.byref(info)))
         return {k: getattr(info, k) for k, _ in NshStepInfo._fields_}
+
+    def set_test_fail_solves(self, k):
+        self._ck(hostlib().nsh_set_test_fail_solves(self.h, int(k)))
 
     def solution(self):
         out = np.empty(self.n_u + self.n_p)

@@ -827,7 +827,7 @@ int gmres(nsb_ctx* c, int max_it, double tol_abs, int n_tmp, int* iterations, do
       precond_apply(c, c->w_tmp.p, w);
       // classical Gram-Schmidt (twice): h = V^T w ; w -= V h
       size_t id = c->prof.begin(PC_ORTH, c->stream);
-      const int passes = c->opt.reorthogonalize ? 2 : 1;
+      const int passes = c->opt.reorthogonalize > 0 ? 2 : 1;
       for (int pass = 0; pass < passes; ++pass) {
         k_multi_dot<<<nb, RED_THREADS, 0, c->stream>>>(k + 1, c->V.p, n, w, n, c->partial.p);
         c->launch_check();
@@ -1344,6 +1344,7 @@ int nsb_set_solver_opts(nsb_handle c, const nsb_solver_opts* o) {
   if (n.cheb_degree_Mp <= 0) n.cheb_degree_Mp = 3;
   if (n.amg_smoother_degree <= 0) n.amg_smoother_degree = 2;
   if (n.schur_mass_coeff == 0.0) n.schur_mass_coeff = -1.0;
+  if (n.reorthogonalize == 0) n.reorthogonalize = 1;   // 0 = default (twice); negative = a single pass
   if (n.precond_precision != 64) n.precond_precision = 32;
   if (n.precond_operator != 1 && n.precond_operator != 2) n.precond_operator = NSB_DEFAULT_PRECOND_OPERATOR;
   const bool changed = n.precond_precision != c->opt.precond_precision || n.precond_operator != c->opt.precond_operator;

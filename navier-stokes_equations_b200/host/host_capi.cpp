@@ -68,6 +68,7 @@ int nsh_create(const char* test_case, const char* mesh_file, const nsh_options* 
     ro.max_steps = o->max_steps;
     if (o->output_dir) ro.output_dir = o->output_dir;
     ro.solver = o->solver;
+    ro.test_fail_solves = o->test_fail_solves;
     dt = o->deltat;
   }
   auto h = std::make_unique<nsh_solver>();
@@ -125,6 +126,12 @@ int nsh_get_solution(nsh_handle h, double* out) {
   std::memcpy(out, s.data(), s.size() * sizeof(double));
   return 0;
   NSH_CATCH
+}
+
+int nsh_set_test_fail_solves(nsh_handle h, int32_t k) {
+  if (!h) return -1;
+  if (h->dim == 2) h->s2->options.test_fail_solves = k; else h->s3->options.test_fail_solves = k;
+  return 0;
 }
 
 nsb_handle nsh_device(nsh_handle h) { return h->dim == 2 ? h->s2->device() : h->s3->device(); }

@@ -129,7 +129,7 @@ template <int dim> void NavierStokes<dim>::setup() {
     ck(nsb_comm_init(dev, (int)mpi_rank, (int)mpi_size, options.nccl_unique_id), "nsb_comm_init");
     const int64_t C = mesh.n_cells();
     part.resize(C);
-    for (int64_t c = 0; c < C; ++c) part[c] = (int32_t)((c * (int64_t)mpi_size) / C);
+    for (int64_t c = 0; c < C; ++c) part[c] = (int32_t)((c * (int64_t)mpi_size) / C);   // output() lists the same chunks
   }
   ck(nsb_set_solver_opts(dev, &options.solver), "nsb_set_solver_opts");
   ck(nsb_upload_mesh(dev, mesh.n_vertices(), mesh.points.data(), mesh.n_cells(), mesh.cells.data(),
@@ -139,7 +139,26 @@ template <int dim> void NavierStokes<dim>::setup() {
   pcout << "Setup complete." << std::endl;
 }
 
+// The C ABI has no forcing input: every test case of the reference uses the identically-zero ForcingTerm
+// (hpp:150-171, TestCases.hpp), and the kernels assemble f = 0 (cpp:683-720).  A user-supplied forcing that is
+// not zero would be silently dropped, so it is rejected here instead (sampled at the mesh vertices, current time
+// and previous time level).
+template <int dim> void NavierStokes<dim>::require_zero_forcing() const {
+  if (!forcing_term || forcing_checked_time == forcing_term->get_time()) return;
+  forcing_checked_time = forcing_term->get_time();
+  const int64_t V = mesh.n_vertices();
+  for (int64_t v = 0; v < V; ++v) {
+    Point<dim> p;
+    for (int d = 0; d < dim; ++d) p[d] = mesh.points[(size_t)v * dim + d];
+    for (unsigned int c = 0; c < (unsigned int)dim; ++c)
+      if (forcing_term->value(p, c) != 0.0)
+        throw std::runtime_error("a non-zero forcing term is not supported by the nsb200 assembly kernels "
+                                 "(the reference's test cases all use the zero ForcingTerm)");
+  }
+}
+
 template <int dim> void NavierStokes<dim>::push_params(bool first_order) {
+  require_zero_forcing();
   nsb_params p;
   p.dt = deltat; p.theta = theta; p.nu = nu; p.rho = rho; p.gamma = 0.1;
   p.use_supg = use_supg ? 1 : 0;
@@ -173,7 +192,8 @@ template <int dim> void NavierStokes<dim>::solve_newton_system() {              
   step_gmres_iterations += it;
   ++step_solves;
   ck(nsb_get_vector(dev, NSB_SOLUTION, newton_update.data()), "nsb_get_vector");
-  if (rc == 1) throw NoConvergence(it, res);
+  const bool forced_fail = options.test_fail_solves > 0 && options.test_fail_solves-- > 0;
+  if (rc == 1 || forced_fail) throw NoConvergence(it, res);
   pcout << "  GMRES (Newton): " << it << " iters" << std::endl;
 }
 
@@ -211,7 +231,8 @@ template <int dim> bool NavierStokes<dim>::solve_linear_system() {              
   last_gmres_iterations = it;
   step_gmres_iterations += it;
   ++step_solves;
-  const bool converged = (rc == 0);
+  const bool forced_fail = options.test_fail_solves > 0 && options.test_fail_solves-- > 0;
+  const bool converged = (rc == 0) && !forced_fail;
   if (!converged)
     pcout << "  WARNING: GMRES did NOT converge after " << it << " iterations, residual = " << res << std::endl;
   ck(nsb_get_vector(dev, NSB_SOLUTION, solution_owned.data()), "nsb_get_vector");
@@ -386,38 +407,49 @@ template <int dim> void NavierStokes<dim>::compute_lift_drag(double& drag_coeff,
 // ------------------------------------------------------------------------------------ output
 template <int dim> void NavierStokes<dim>::output(const unsigned int time_step) {    // cpp:1013-1042
   if (!options.write_vtu) return;
-  // solution_NNNN.<rank>.vtu + solution_NNNN.pvtu: velocity (vector), pressure, subdomain on the P1 vertices
+  // One piece per rank holding that rank's OWNED cells (DataOut::write_vtu_with_pvtu_record, cpp:1037-1041):
+  // solution_NNNN.<rank>.vtu with velocity (vector), pressure and subdomain, and solution_NNNN.pvtu on rank 0
+  // listing every piece.  Ownership = the contiguous cell chunks handed to nsb_upload_mesh in setup().
   const int NV = dim + 1;
+  const int64_t C = mesh.n_cells();
+  const int64_t c0 = (C * (int64_t)mpi_rank + mpi_size - 1) / mpi_size, c1 = (C * (int64_t)(mpi_rank + 1) + mpi_size - 1) / mpi_size;
+  // vertices used by the owned cells, renumbered in order of first use
+  std::vector<int64_t> vmap((size_t)mesh.n_vertices(), -1), vlist;
+  for (int64_t c = c0; c < c1; ++c)
+    for (int k = 0; k < NV; ++k) {
+      const uint32_t v = mesh.cells[(size_t)c * NV + k];
+      if (vmap[v] < 0) { vmap[v] = (int64_t)vlist.size(); vlist.push_back(v); }
+    }
   char name[256];
   std::snprintf(name, sizeof(name), "%ssolution_%04u.%u.vtu", options.output_dir.c_str(), time_step, mpi_rank);
   std::ofstream f(name);
-  const int64_t V = mesh.n_vertices(), C = mesh.n_cells();
+  const int64_t V = (int64_t)vlist.size(), CL = c1 - c0;
   f << std::setprecision(9);
   f << "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<UnstructuredGrid>\n";
-  f << "<Piece NumberOfPoints=\"" << V << "\" NumberOfCells=\"" << C << "\">\n<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n";
-  for (int64_t v = 0; v < V; ++v) {
-    for (int k = 0; k < 3; ++k) f << (k < dim ? mesh.points[(size_t)v * dim + k] : 0.0) << " ";
+  f << "<Piece NumberOfPoints=\"" << V << "\" NumberOfCells=\"" << CL << "\">\n<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n";
+  for (int64_t i = 0; i < V; ++i) {
+    for (int k = 0; k < 3; ++k) f << (k < dim ? mesh.points[(size_t)vlist[i] * dim + k] : 0.0) << " ";
     f << "\n";
   }
   f << "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int64\" Name=\"connectivity\" format=\"ascii\">\n";
-  for (int64_t c = 0; c < C; ++c) {
-    for (int k = 0; k < NV; ++k) f << mesh.cells[(size_t)c * NV + k] << " ";
+  for (int64_t c = c0; c < c1; ++c) {
+    for (int k = 0; k < NV; ++k) f << vmap[mesh.cells[(size_t)c * NV + k]] << " ";
     f << "\n";
   }
   f << "</DataArray>\n<DataArray type=\"Int64\" Name=\"offsets\" format=\"ascii\">\n";
-  for (int64_t c = 0; c < C; ++c) f << (c + 1) * NV << "\n";
+  for (int64_t c = 0; c < CL; ++c) f << (c + 1) * NV << "\n";
   f << "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n";
-  for (int64_t c = 0; c < C; ++c) f << (dim == 2 ? 5 : 10) << "\n";
+  for (int64_t c = 0; c < CL; ++c) f << (dim == 2 ? 5 : 10) << "\n";
   f << "</DataArray>\n</Cells>\n<PointData Vectors=\"velocity\" Scalars=\"pressure\">\n";
   f << "<DataArray type=\"Float64\" Name=\"velocity\" NumberOfComponents=\"3\" format=\"ascii\">\n";
-  for (int64_t v = 0; v < V; ++v) {
-    for (int k = 0; k < 3; ++k) f << (k < dim ? current_solution[dof_handler.vertex_dof0[v] + k] : 0.0) << " ";
+  for (int64_t i = 0; i < V; ++i) {
+    for (int k = 0; k < 3; ++k) f << (k < dim ? current_solution[dof_handler.vertex_dof0[vlist[i]] + k] : 0.0) << " ";
     f << "\n";
   }
   f << "</DataArray>\n<DataArray type=\"Float64\" Name=\"pressure\" format=\"ascii\">\n";
-  for (int64_t v = 0; v < V; ++v) f << current_solution[dof_handler.vertex_pdof[v]] << "\n";
+  for (int64_t i = 0; i < V; ++i) f << current_solution[dof_handler.vertex_pdof[vlist[i]]] << "\n";
   f << "</DataArray>\n</PointData>\n<CellData>\n<DataArray type=\"Float32\" Name=\"subdomain\" format=\"ascii\">\n";
-  for (int64_t c = 0; c < C; ++c) f << (mpi_size > 1 ? (c * (int64_t)mpi_size) / C : 0) << "\n";
+  for (int64_t c = 0; c < CL; ++c) f << mpi_rank << "\n";
   f << "</DataArray>\n</CellData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n";
   if (mpi_rank == 0) {
     std::snprintf(name, sizeof(name), "%ssolution_%04u.pvtu", options.output_dir.c_str(), time_step);
@@ -425,9 +457,12 @@ template <int dim> void NavierStokes<dim>::output(const unsigned int time_step) 
     p << "<?xml version=\"1.0\"?>\n<VTKFile type=\"PUnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<PUnstructuredGrid GhostLevel=\"0\">\n";
     p << "<PPointData Vectors=\"velocity\" Scalars=\"pressure\">\n<PDataArray type=\"Float64\" Name=\"velocity\" NumberOfComponents=\"3\"/>\n<PDataArray type=\"Float64\" Name=\"pressure\"/>\n</PPointData>\n";
     p << "<PCellData>\n<PDataArray type=\"Float32\" Name=\"subdomain\"/>\n</PCellData>\n<PPoints>\n<PDataArray type=\"Float64\" NumberOfComponents=\"3\"/>\n</PPoints>\n";
-    char piece[128];
-    std::snprintf(piece, sizeof(piece), "solution_%04u.0.vtu", time_step);
-    p << "<Piece Source=\"" << piece << "\"/>\n</PUnstructuredGrid>\n</VTKFile>\n";
+    for (unsigned int r = 0; r < mpi_size; ++r) {
+      char piece[128];
+      std::snprintf(piece, sizeof(piece), "solution_%04u.%u.vtu", time_step, r);
+      p << "<Piece Source=\"" << piece << "\"/>\n";
+    }
+    p << "</PUnstructuredGrid>\n</VTKFile>\n";
   }
 }
 

@@ -78,6 +78,8 @@ struct RunOptions {
   int max_steps = -1;             // stop run() after this many time steps (-1: until T)
   std::string output_dir = "./";
   nsb_solver_opts solver{};       // zero = library defaults
+  int test_fail_solves = 0;       // test hook: the next k linear solves are REPORTED as not converged (their result is kept,
+                                  // as the reference keeps the iterate of a failed GMRES) -> drives run()'s retry / fallback paths
 };
 
 struct StepInfo {
@@ -187,8 +189,10 @@ protected:
   unsigned int time_step_no = 0;
   int last_gmres_iterations = 0, step_gmres_iterations = 0, step_solves = 0;
   double last_rhs_norm = 0.0;
+  mutable double forcing_checked_time = -1.0;
 
   void push_params(bool first_order);
+  void require_zero_forcing() const;
   void build_system_constraints();
   void ck(int rc, const char* what) const;
   std::function<double(const double*, int)> eval(const std::shared_ptr<Function<dim>>& f) const;

@@ -300,3 +300,43 @@ def assemble(mesh, dm, pattern, p: Params, con, kind, vec_a, vec_b, with_pressur
 def to_csr(pattern, values, N):
     rowptr, col = pattern
     return sp.csr_matrix((values, col, rowptr), shape=(N, N))
+
+
+def pressure_blocks(mesh, dm, con):
+    """(1,1) blocks of pressure_mass / pressure_stiffness (cpp:798-803, 812-829) as ONE compact CSR over the pressure
+    DoFs: returns (ptr int64, col int32, Mp, Kp), identical to the (1,1) blocks of assemble(...).Mp / .Kp.
+    M_p,ij = sum_q psi_i psi_j JxW, K_p,ij = sum_q grad psi_i . grad psi_j JxW, both through the matrix-only
+    distribute_local_to_global (constrained rows / columns dropped, |m_cc| on the diagonal -- never zero here, so the
+    average-diagonal branch of A.5 is not taken), then K_p += 1e-6 M_p.  Vectorised over the cells so that the
+    multi-million-cell meshes of the CPU baseline do not need two more full-pattern value arrays."""
+    dim = mesh.dim
+    nv = dim + 1
+    geom = CellGeometry(mesh)
+    pts, w = fe.quadrature(dim)
+    lam = fe.barycentric(pts)                                    # (Q, nv): P1 shape values
+    mhat = np.einsum("q,qi,qj->ij", w, lam, lam)                 # reference mass matrix with the reference's rule
+    node, comp = fe.local_dof_layout(dim)
+    ploc = np.array([k for k in range(node.shape[0]) if comp[k] == dim])
+    ploc = ploc[np.argsort(node[ploc])]                          # local pressure DoF of vertex 0..dim
+    pid = dm.cell_dofs[:, ploc].astype(np.int64) - dm.n_u        # (C, nv)
+    gl = geom.grad_lambda
+    cm = geom.detJ[:, None, None] * mhat[None, :, :]
+    ck = np.zeros_like(cm)
+    for q in range(len(w)):                                      # same summation order as the cell loop
+        ck += np.einsum("cid,cjd->cij", gl, gl) * (w[q] * geom.detJ)[:, None, None]
+    isc = con.is_c[dm.n_u + pid]                                 # (C, nv)
+    drop = isc[:, :, None] | isc[:, None, :]
+    idx = np.arange(nv)
+    out = []
+    for loc in (cm, ck):
+        o = np.where(drop, 0.0, loc)
+        o[:, idx, idx] = np.where(isc, np.abs(loc[:, idx, idx]), o[:, idx, idx])
+        out.append(o)
+    ii = np.repeat(pid, nv, axis=1).ravel()
+    jj = np.tile(pid, (1, nv)).ravel()
+    n_p = dm.n_p
+    Mp = sp.coo_matrix((out[0].ravel(), (ii, jj)), shape=(n_p, n_p)).tocsr()
+    Kp = sp.coo_matrix((out[1].ravel(), (ii, jj)), shape=(n_p, n_p)).tocsr()
+    Mp.sort_indices(); Kp.sort_indices()
+    assert np.array_equal(Mp.indptr, Kp.indptr) and np.array_equal(Mp.indices, Kp.indices)
+    return Mp.indptr.astype(np.int64), Mp.indices.astype(np.int32), Mp.data.copy(), Kp.data + 1e-6 * Mp.data

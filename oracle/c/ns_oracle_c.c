@@ -580,29 +580,38 @@ static void kp_solve(const csr_t *Kp, const ilu_t *Fk, const double *t, double *
 }
 
 /* ------------------------------------------------------------------ solve_linear_system */
-int nso_solve(int64_t N, int64_t n_u, const int64_t *rowptr, const int32_t *col, const double *A, const double *Mp,
-              const double *Kp, const double *b, double nu, double rho, double deltat, double theta, int max_it,
-              double tol_rel, int n_tmp_vectors, int nblocks, double schur_mass_coeff, double kp_tol, double *x, int *iterations,
-              double *residual) {
+/* Core: A as full scalar CSR (used in place, not copied), the (1,1) blocks of M_p / K_p as a compact CSR over the pressure
+ * DoFs (shared pattern pp_ptr / pp_col).  time_budget_s > 0: stop iterating once the solve has run that long (the result is
+ * then reported as not converged; bench.py's reference arm uses it to stay inside its time limit).
+ * timings[4] (optional) = {preconditioner setup, GMRES iterations, K_p CG inside them, total} in seconds. */
+int nso_solve_blocks(int64_t N, int64_t n_u, const int64_t *rowptr, const int32_t *col, const double *A, const int64_t *pp_ptr,
+                     const int32_t *pp_col, const double *Mp, const double *Kp, const double *b, double nu, double rho,
+                     double deltat, double theta, int max_it, double tol_rel, int n_tmp_vectors, int nblocks,
+                     double schur_mass_coeff, double kp_tol, double time_budget_s, double *x, int *iterations, double *residual,
+                     double *timings) {
   /* schur_mass_coeff < 0: the reference's theta*nu (hpp:342); >= 0: override (the product's default is theta*nu + gamma) */
   const double cmass = schur_mass_coeff >= 0 ? schur_mass_coeff : theta * nu;
   const int64_t n_p = N - n_u;
   if (nblocks < 1) nblocks = 1;
   csr_t Af, F, B, Mpp, Kpp;
-  csr_block(rowptr, col, A, 0, N, 0, N, &Af);
-  csr_block(rowptr, col, A, 0, n_u, 0, n_u, &F);
-  csr_block(rowptr, col, A, n_u, N, 0, n_u, &B);
-  csr_block(rowptr, col, Mp, n_u, N, n_u, N, &Mpp);
-  csr_block(rowptr, col, Kp, n_u, N, n_u, N, &Kpp);
+  Af.n = (int)N; Af.ptr = (int64_t *)rowptr; Af.col = (int32_t *)col; Af.val = (double *)A;     /* borrowed */
+  Mpp.n = Kpp.n = (int)n_p;
+  Mpp.ptr = Kpp.ptr = (int64_t *)pp_ptr; Mpp.col = Kpp.col = (int32_t *)pp_col;
+  Mpp.val = (double *)Mp; Kpp.val = (double *)Kp;
+  const double t_setup0 = omp_get_wtime();
   /* PreconditionBlockTriangular::initialize -- every solve (hpp:282-318) */
   ilu_t iF, iM, iK;
-  const double t_setup0 = omp_get_wtime();
+  csr_block(rowptr, col, A, 0, n_u, 0, n_u, &F);
   ilu_setup(&iF, F.n, F.ptr, F.col, F.val, 1, nblocks);
+  const long long nnzF = (long long)F.ptr[F.n];
+  csr_free(&F);                                          /* only the factors are needed from here on */
+  csr_block(rowptr, col, A, n_u, N, 0, n_u, &B);
   ilu_setup(&iM, Mpp.n, Mpp.ptr, Mpp.col, Mpp.val, 0, nblocks);
   ilu_setup(&iK, Kpp.n, Kpp.ptr, Kpp.col, Kpp.val, 0, nblocks);
-  if (getenv("NSO_DEBUG")) fprintf(stderr, "[nso] ilu setup %.3f s, nnz(F)=%lld nnz(ILU1)=%lld\n", omp_get_wtime() - t_setup0, (long long)F.ptr[F.n], (long long)iF.ptr[iF.n]);
+  const double t_setup = omp_get_wtime() - t_setup0;
+  if (getenv("NSO_DEBUG")) fprintf(stderr, "[nso] ilu setup %.3f s, nnz(F)=%lld nnz(ILU1)=%lld\n", t_setup, nnzF, (long long)iF.ptr[iF.n]);
   const int m = n_tmp_vectors - 2 > 1 ? n_tmp_vectors - 2 : 1;
-  double *V = (double *)malloc(sizeof(double) * (size_t)(m + 1) * N);
+  double *V = (double *)malloc(sizeof(double) * (size_t)(m + 1) * N);      /* pages are touched as the basis grows */
   double *w = (double *)malloc(sizeof(double) * N), *tmp = (double *)malloc(sizeof(double) * N);
   double *tp = (double *)malloc(sizeof(double) * n_p), *t2 = (double *)malloc(sizeof(double) * n_p), *y1 = (double *)malloc(sizeof(double) * n_p);
   double *wk = (double *)malloc(sizeof(double) * 4 * n_p);
@@ -622,7 +631,7 @@ int nso_solve(int64_t N, int64_t n_u, const int64_t *rowptr, const int32_t *col,
   double t_kp = 0;
   memset(x, 0, sizeof(double) * N);
   const double tol = tol_rel * sqrt(dotp(N, b, b));
-  int it = 0, rc = 1, first = 1;
+  int it = 0, rc = 1, first = 1, out_of_time = 0;
   double res = 0;
   for (;;) {
     if (first) { PRECOND(b, w); }
@@ -635,6 +644,7 @@ int nso_solve(int64_t N, int64_t n_u, const int64_t *rowptr, const int32_t *col,
     res = beta;
     if (first && beta <= tol) { rc = 0; break; }
     first = 0;
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < N; ++i) V[i] = w[i] / beta;
     memset(g, 0, sizeof(double) * (m + 1));
     g[0] = beta;
@@ -652,8 +662,10 @@ int nso_solve(int64_t N, int64_t n_u, const int64_t *rowptr, const int32_t *col,
       }
       const double hn = sqrt(dotp(N, vn, vn));
       H[(size_t)(k + 1) * m + k] = hn;
-      if (hn > 0)
+      if (hn > 0) {
+#pragma omp parallel for schedule(static)
         for (int64_t j = 0; j < N; ++j) vn[j] /= hn;
+      }
       for (int i = 0; i < k; ++i) {
         const double t = cs[i] * H[(size_t)i * m + k] + sn[i] * H[(size_t)(i + 1) * m + k];
         H[(size_t)(i + 1) * m + k] = -sn[i] * H[(size_t)i * m + k] + cs[i] * H[(size_t)(i + 1) * m + k];
@@ -669,6 +681,7 @@ int nso_solve(int64_t N, int64_t n_u, const int64_t *rowptr, const int32_t *col,
       if (getenv("NSO_DEBUG") && it % 10 == 0) fprintf(stderr, "[nso] it %d res %.4e (tol %.4e)\n", it, res, tol);
       if (res <= tol) { conv = 1; break; }
       if (it >= max_it) break;
+      if (time_budget_s > 0 && omp_get_wtime() - t_setup0 > time_budget_s) { out_of_time = 1; break; }
     }
     for (int i = kused - 1; i >= 0; --i) {
       double s = g[i];
@@ -677,17 +690,40 @@ int nso_solve(int64_t N, int64_t n_u, const int64_t *rowptr, const int32_t *col,
     }
     for (int i = 0; i < kused; ++i) {
       const double *vi = V + (size_t)i * N;
+#pragma omp parallel for schedule(static)
       for (int64_t j = 0; j < N; ++j) x[j] += yv[i] * vi[j];
     }
     if (conv) { rc = 0; break; }
-    if (it >= max_it) break;
+    if (it >= max_it || out_of_time) break;
   }
-  if (getenv("NSO_DEBUG")) fprintf(stderr, "[nso] total %.3f s, of which K_p CG %.3f s\n", omp_get_wtime() - t_setup0, t_kp);
+  const double t_total = omp_get_wtime() - t_setup0;
+  if (getenv("NSO_DEBUG")) fprintf(stderr, "[nso] total %.3f s, of which K_p CG %.3f s\n", t_total, t_kp);
+  if (timings) { timings[0] = t_setup; timings[1] = t_total - t_setup; timings[2] = t_kp; timings[3] = t_total; }
   *iterations = it; *residual = res;
   free(V); free(w); free(tmp); free(tp); free(t2); free(y1); free(wk); free(H); free(cs); free(sn); free(g); free(yv);
   ilu_free(&iF); ilu_free(&iM); ilu_free(&iK);
-  csr_free(&Af); csr_free(&F); csr_free(&B); csr_free(&Mpp); csr_free(&Kpp);
+  csr_free(&B);
+  return out_of_time ? 2 : rc;
+}
+
+/* M_p / K_p given on the FULL pattern (as assemble_impl writes them): extract the (1,1) blocks and solve. */
+int nso_solve(int64_t N, int64_t n_u, const int64_t *rowptr, const int32_t *col, const double *A, const double *Mp,
+              const double *Kp, const double *b, double nu, double rho, double deltat, double theta, int max_it,
+              double tol_rel, int n_tmp_vectors, int nblocks, double schur_mass_coeff, double kp_tol, double *x, int *iterations,
+              double *residual) {
+  csr_t Mpp, Kpp;
+  csr_block(rowptr, col, Mp, n_u, N, n_u, N, &Mpp);
+  csr_block(rowptr, col, Kp, n_u, N, n_u, N, &Kpp);
+  const int rc = nso_solve_blocks(N, n_u, rowptr, col, A, Mpp.ptr, Mpp.col, Mpp.val, Kpp.val, b, nu, rho, deltat, theta, max_it,
+                                  tol_rel, n_tmp_vectors, nblocks, schur_mass_coeff, kp_tol, 0.0, x, iterations, residual, NULL);
+  csr_free(&Mpp); csr_free(&Kpp);
   return rc;
+}
+
+void nso_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#endif
 }
 
 int nso_num_threads(void) {

@@ -29,6 +29,7 @@ def lib():
         _lib = ctypes.CDLL(LIB)
         _lib.nso_num_threads.restype = ctypes.c_int
         _lib.nso_solve.restype = ctypes.c_int
+        _lib.nso_solve_blocks.restype = ctypes.c_int
     return _lib
 
 
@@ -112,3 +113,31 @@ def solve(pattern, N, n_u, A, Mp, Kp, b, p, max_it=200, tol_rel=1e-2, n_tmp_vect
                          ctypes.c_int(max_it), ctypes.c_double(tol_rel), ctypes.c_int(n_tmp_vectors), ctypes.c_int(nblocks), ctypes.c_double(schur_mass_coeff), ctypes.c_double(kp_tol),
                          _p(x), ctypes.byref(it), ctypes.byref(res))
     return x, it.value, res.value, rc == 0
+
+
+def solve_blocks(pattern, N, n_u, A, pp, b, p, max_it=200, tol_rel=1e-2, n_tmp_vectors=150, nblocks=None, schur_mass_coeff=-1.0,
+                 kp_tol=1e-4, time_budget_s=0.0):
+    """solve_linear_system() with M_p / K_p given as the compact pressure-block CSR of oracle.assemble.pressure_blocks
+    (pp = (ptr, col, Mp, Kp)); A is used in place.  Returns (x, iterations, residual, status, timings) with status
+    0 converged / 1 max_it reached / 2 stopped by time_budget_s, timings = dict(setup, gmres, kp_cg, total) seconds."""
+    rowptr, col = pattern
+    assert rowptr.dtype == np.int64 and col.dtype == np.int32 and rowptr.flags.c_contiguous and col.flags.c_contiguous
+    pptr, pcol, Mp, Kp = pp
+    x = np.zeros(N)
+    it = ctypes.c_int(0)
+    res = ctypes.c_double(0)
+    tm = np.zeros(4)
+    if nblocks is None:
+        nblocks = num_threads()
+    rc = lib().nso_solve_blocks(ctypes.c_int64(N), ctypes.c_int64(n_u), _p(rowptr), _p(col), _p(A), _p(np.ascontiguousarray(pptr, np.int64)),
+                                _p(np.ascontiguousarray(pcol, np.int32)), _p(np.ascontiguousarray(Mp)), _p(np.ascontiguousarray(Kp)), _p(b),
+                                ctypes.c_double(p.nu), ctypes.c_double(p.rho), ctypes.c_double(p.dt), ctypes.c_double(p.theta),
+                                ctypes.c_int(max_it), ctypes.c_double(tol_rel), ctypes.c_int(n_tmp_vectors), ctypes.c_int(nblocks),
+                                ctypes.c_double(schur_mass_coeff), ctypes.c_double(kp_tol), ctypes.c_double(time_budget_s),
+                                _p(x), ctypes.byref(it), ctypes.byref(res), _p(tm))
+    return x, it.value, res.value, rc, dict(setup=tm[0], gmres=tm[1], kp_cg=tm[2], total=tm[3])
+
+
+def set_num_threads(n):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline must use the host cores regardless."""
+    lib().nso_set_num_threads(ctypes.c_int(int(n)))

@@ -154,6 +154,7 @@ class Oracle:
         self.Mp = self.Kp = None
         self.newton_constraints = odofs.build_constraints(mesh, self.dm, None, self.ids, homogeneous=True)
         self.gmres_iters = []
+        self.fail_solves = 0      # test hook: report the next k solves as not converged (their result is kept)
 
     # -- pieces -------------------------------------------------------------------
     def inlet(self, t):
@@ -202,7 +203,11 @@ class Oracle:
         A = asm.to_csr(self.pattern, out.A, N)
         if self.solver == "direct":
             x = direct_solve(A, out.b)
-            return con.distribute(x), True, 0
+            ok = True
+            if self.fail_solves > 0:
+                self.fail_solves -= 1
+                ok = False
+            return con.distribute(x), ok, 0
         P = BlockTriangular(A, asm.to_csr(self.pattern, self.Mp, N), asm.to_csr(self.pattern, self.Kp, N),
                             self.dm.n_u, p.nu, p.rho, p.dt, p.theta)
         tol = 1e-2 * np.linalg.norm(out.b)

@@ -1,4 +1,3 @@
-import importlib.util
 import os
 import sys
 
@@ -18,15 +17,9 @@ def pytest_configure(config):
 
 
 def load_nsb():
-    """Import navier-stokes_equations_b200/__init__.py by path (the directory name is not an identifier)."""
-    name = "nsb200_pkg"
-    if name in sys.modules:
-        return sys.modules[name]
-    spec = importlib.util.spec_from_file_location(name, os.path.join(PKG_DIR, "__init__.py"))
-    mod = importlib.util.module_from_spec(spec)
-    sys.modules[name] = mod
-    spec.loader.exec_module(mod)
-    return mod
+    """The product package (navier-stokes_equations_b200/, loaded by path through the root module nsb200.py)."""
+    import nsb200
+    return nsb200
 
 
 @pytest.fixture(scope="session")

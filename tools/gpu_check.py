@@ -1,6 +1,5 @@
 """Developer harness: CUDA path vs the numpy oracle on one GPU (prints errors, no asserts).
 Usage: python -m tools.gpu_check [2d|3d|all]"""
-import importlib.util
 import os
 import sys
 import time
@@ -15,10 +14,8 @@ from tools import meshgen, msh  # noqa: E402
 
 
 def load_nsb():
-    spec = importlib.util.spec_from_file_location("nsb200", os.path.join(ROOT, "navier-stokes_equations_b200", "__init__.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod
+    import nsb200
+    return nsb200
 
 
 def relerr(a, b):
