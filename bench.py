@@ -83,12 +83,12 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons}
 
 
-def recorded_traffic(level, kernel):
+def recorded_traffic(level, kernel, precision=32):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-    (profiles/r01_traffic.json); None when no capture exists for this workload / kernel."""
+    (profiles/r02_traffic.json, keys level -> kernel[_fp<precision>]); None when no capture exists for this workload / kernel."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        return t[str(level)][kernel]
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[str(level)]
+        return t.get("%s_fp%d" % (kernel, precision), t.get(kernel))
     except Exception:
         return None
 
@@ -152,9 +152,11 @@ class CpuCase:
                                                   n_tmp_vectors=150, time_budget_s=time_budget_s)
         t2 = time.time()
         r = dict(seconds=t2 - t0, assembly_s=t1 - t0, solve_s=t2 - t1, precond_setup_s=float(tm["setup"]), gmres_s=float(tm["gmres"]),
-                 kp_cg_s=float(tm["kp_cg"]), gmres_iterations=int(its), converged=(rc == 0), stopped_by_time_budget=(rc == 2))
+                 kp_cg_s=float(tm["kp_cg"]), gmres_iterations=int(its), converged=(rc == 0), stopped_by_time_budget=(rc == 2),
+                 breakdown_nan=(rc == 3))
         log("[bench] cpu step: assembly %.1f s, ILU setup %.1f s, GMRES %.1f s (%d its, converged %s%s), K_p CG %.1f s"
-            % (r["assembly_s"], r["precond_setup_s"], r["gmres_s"], its, rc == 0, ", STOPPED BY TIME BUDGET" if rc == 2 else "", r["kp_cg_s"]))
+            % (r["assembly_s"], r["precond_setup_s"], r["gmres_s"], its, rc == 0,
+               ", STOPPED BY TIME BUDGET" if rc == 2 else ", RESIDUAL IS NaN (ILU(1) breakdown)" if rc == 3 else "", r["kp_cg_s"]))
         return r
 
 
@@ -217,7 +219,11 @@ def reference_arm(args):
                         "(K_p CG %.1f); %d its, converged=%s%s%s"
                         % (level, mesh.n_cells, case.dm.n_dofs, case.pat[1].size, r["seconds"], r["assembly_s"], r["precond_setup_s"],
                            r["gmres_s"], r["kp_cg_s"], r["gmres_iterations"], r["converged"],
-                           "; GMRES stopped early by the arm's time budget, so the step time is a LOWER bound" if r["stopped_by_time_budget"] else "",
+                           "; GMRES stopped early by the arm's time budget, so the step time is a LOWER bound" if r["stopped_by_time_budget"] else
+                           "; the ILU(1) factors of F overflow on this mesh (no pivoting, Ifpack defaults) and the residual is NaN from the first "
+                           "iteration -- deal.II's SolverControl reports failure on a NaN residual, so the time is that of the reference's FIRST "
+                           "attempt only (its BE fallback and dt-halving retries would repeat assembly + factorization up to 6 more times): a LOWER bound"
+                           if r["breakdown_nan"] else "",
                            "; NOT the requested mesh (%s): scaled by cells" % note if not same else ""))}
     line = {
         "impl": "reference", "metric": "time-steps/s", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
@@ -266,8 +272,8 @@ def main():
     ap.add_argument("--level", type=int, default=20, help="mesh-3D-<level>-equivalent (5, 10, 20, 40)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--operator", type=int, default=0,
-                    help="operator inside the velocity polynomial: 1 assembled fp32 copy, 2 element-wise, 0 library default")
+    ap.add_argument("--precision", type=int, default=0,
+                    help="storage of the packed operator inside the velocity polynomial: 16, 32 (or 64: the fp64 values); 0 = library default")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -313,8 +319,8 @@ def main():
     n_u, n_p, N = hs.n_u, hs.n_p, hs.n_dofs
     log("[bench] rank %d host setup %.1f s: %d cells, %d + %d DoFs" % (rank, time.time() - t0, hs.n_cells, n_u, n_p))
     dev = nsb.Device(3, local_rank)
-    if args.operator:
-        dev.set_solver_opts(precond_operator=args.operator)
+    if args.precision:
+        dev.set_solver_opts(precond_precision=args.precision)
     part = None
     if world > 1:
         dev.comm_init(rank, world, uid)
@@ -403,51 +409,70 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        # dominant kernel: the velocity-block SpMV (polynomial preconditioner).  Algorithmic bytes per
-        # 12 nnz + 16 n + 4 (n+1), on the block it multiplies (F = A(0,0)).
         tot = {k: v[0] for k, v in prof.items()}
         dom = max(("spmv_vel", "spmv", "asm_rows", "orth"), key=lambda k: tot.get(k, 0.0))
         blocks = dev.block_nnz()
         opts_eff = dev.get_solver_opts()
-        bytes_alg = {
+        vop = dev.velocity_operator_info()
+        # Bytes per launch, two conventions:
+        #  * "performed": what the operation has to move AS IT IS PERFORMED -- the stored operator (packed fp32 / fp16 copy for
+        #    the velocity block, fp64 values for A), its compressed index side, and each vector once;
+        #  * "csr": SURVEY 8(d)'s figure for a textbook fp64 CSR SpMV (12 B per non-zero + vectors), kept for reference only.
+        n_loc_u = n_u if world == 1 else int(nrows * n_u / N)      # owned velocity rows (exact on one GPU)
+        vec_vel = (8 + 8 + 8 + 16) * n_loc_u              # x read, y write, u read, poly read + write
+        bytes_perf = {
+            "spmv_vel": (vop["value_bytes"] + vop["index_bytes"] if vop["precision"] != 64 else 8 * blocks["uu"] + 2 * blocks["uu"] // 9) + vec_vel,
+            "spmv": 8 * nnz + 2 * (blocks["uu"] // 9 + blocks["up"]) + 32 * (nrows // 3) + 16 * nrows,
+            "asm_rows": 8 * nnz + 8 * nrows + 8 * 3 * 4 * nc + 20 * 34 * nc,
+        }
+        bytes_csr = {
+            "spmv_vel": 12 * blocks["uu"] + 16 * n_loc_u + 4 * (n_loc_u + 1),
             "spmv": 12 * nnz + 16 * nrows + 4 * (nrows + 1),
-            "spmv_vel": None,
             "asm_rows": 8 * nnz + 8 * nrows + 8 * 3 * 4 * nc + 20 * 34 * nc,
         }
         kernels = {}
         for k, (t_ms, n) in prof.items():
             if n:
                 kernels[k] = {"ms_total": round(t_ms, 3), "launches": n, "ms_avg": round(t_ms / n, 4)}
+        prec = opts_eff["precond_precision"]
         line = {
             "metric": "time-steps/s", "value": args.steps / (ms * 1e-3), "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64" + (" (fp%d operator copy inside the velocity preconditioner)" % prec if prec != 64 else ""),
+            "data": "synthetic",
             "config": {"workload": workload_name(args.level, hs.n_cells, N, nnz_global),
                        "parallelism": "1 process per GPU, contiguous cell chunks" if world > 1 else "single GPU",
                        "l2": "inputs (%.1f GB of matrix values) exceed L2; no flush needed" % (8e-9 * nnz),
                        "gmres_iterations_per_step": iters,
-                       "solver": dict(dev.solver_info(), velocity_operator={1: "assembled fp%d copy" % opts_eff["precond_precision"],
-                                                                            2: "element-wise (S rows fp32 + cell geometry)"}[opts_eff["precond_operator"]])},
+                       "solver": dict(dev.solver_info(), velocity_operator="packed fp%d copy of Dinv F, TMA-streamed" % prec if prec != 64 else "assembled fp64 values",
+                                      velocity_operator_bytes=vop)},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": int(2 * 8 * N + 12 * cdofs.size),
                     "d2h_bytes_per_step": int(8 * N)},
             "kernels": kernels,
         }
+        for k in ("spmv_vel", "spmv", "asm_rows"):
+            if k in kernels:
+                kernels[k]["performed_GBps"] = round(bytes_perf[k] / (kernels[k]["ms_avg"] * 1e-3) / 1e9, 1)
+                kernels[k]["frac_of_peak"] = round(kernels[k]["performed_GBps"] / peak, 3)
+        if "asm_rows" in kernels:
+            t_asm = sum(kernels[k]["ms_avg"] for k in ("asm_context", "asm_rows", "asm_pack") if k in kernels)
+            kernels["asm_rows"]["all_passes_ms"] = round(t_asm, 3)
+            kernels["asm_rows"]["all_passes_frac_of_peak"] = round(bytes_perf["asm_rows"] / (t_asm * 1e-3) / 1e9 / peak, 3)
         # roofline of the dominant kernel
-        bytes_alg["spmv_vel"] = 12 * blocks["uu"] + 16 * n_u + 4 * (n_u + 1)
-        if dom in kernels and bytes_alg.get(dom):
-            ach = bytes_alg[dom] / (kernels[dom]["ms_avg"] * 1e-3) / 1e9
+        if dom in kernels and bytes_perf.get(dom):
+            ach = bytes_perf[dom] / (kernels[dom]["ms_avg"] * 1e-3) / 1e9
+            tr = recorded_traffic(args.level, dom, prec) if world == 1 else None
             line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                "traffic": recorded_traffic(args.level, dom + ("_ebe" if dom == "spmv_vel" and opts_eff["precond_operator"] == 2 else "")) if world == 1 else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_alg[dom])}
-            tr = line["roofline"]["traffic"]
+                                "traffic": tr, "peak_source": peak_src,
+                                "bytes_per_launch": int(bytes_perf[dom]),
+                                "bytes_convention": "operation as performed: stored operator (packed fp%s values + metadata) + each vector once" % prec,
+                                "frac_csr_convention": bytes_csr[dom] / (kernels[dom]["ms_avg"] * 1e-3) / 1e9 / peak}
             if tr:
-                # what the kernel really moves (compressed indices, fp32 operator copy) against the same peak
                 line["roofline"]["dram_GBps"] = tr / (kernels[dom]["ms_avg"] * 1e-3) / 1e9
                 line["roofline"]["dram_frac"] = line["roofline"]["dram_GBps"] / peak
-        for k in ("spmv", "asm_rows"):
-            if k in kernels:
-                kernels[k]["algorithmic_GBps"] = round(bytes_alg[k] / (kernels[k]["ms_avg"] * 1e-3) / 1e9, 1)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_for(args.level, hs.n_cells)
         sys.stdout.flush()

@@ -50,13 +50,12 @@ typedef struct nsb_solver_opts {
   double schur_mass_coeff;  /* coefficient of M_p^-1; <0 = theta*nu + gamma_graddiv (default),
                                set to theta*nu for the reference's exact scaling (hpp:343) */
   int32_t reorthogonalize;  /* 0 or 1 = classical Gram-Schmidt twice (default), <0 = once  */
-  int32_t precond_precision;/* storage of the operator used INSIDE the velocity polynomial: 32 (default; products are
-                               accumulated in fp64, so the preconditioner stays a fixed linear operator) or 64.
-                               Changing it invalidates the assembled system (re-assemble before solving). */
-  int32_t precond_operator; /* how that operator is applied: 1 = from an assembled copy of the velocity block (precision above);
-                               2 = element-wise from per-cell rows S_e[a][:] (fp32) + the cell geometry, 2.4x fewer bytes
-                               per application; linearised systems only, Newton systems use the assembled fp64 values.
-                               0 = library default.  Changing it invalidates the assembled system. */
+  int32_t precond_precision;/* storage of the operator used INSIDE the velocity polynomial: a packed, tile-planar copy of
+                               Dinv F in fp32 (32, default) or fp16 (16), streamed through shared memory with TMA bulk copies
+                               (products and sums in fp64, so the preconditioner stays a fixed linear operator), or 64 = the
+                               assembled fp64 values themselves.  Changing it invalidates the assembled system
+                               (re-assemble before solving). */
+  int32_t precond_operator; /* reserved (round 1's element-wise operator was removed); ignored */
 } nsb_solver_opts;
 
 /* ---- lifetime -------------------------------------------------------------------- */
@@ -150,13 +149,17 @@ int nsb_timer_start(nsb_handle h);
 int nsb_timer_stop(nsb_handle h, double* milliseconds);
 int nsb_synchronize(nsb_handle h);
 /* per-kernel-class CUDA-event profile: names "asm_context","asm_rows","spmv","spmv_vel",
- * "schur","amg","orth","other" */
+ * "schur","amg","orth","other","asm_pack" */
 int nsb_profile_enable(nsb_handle h, int on);
 int nsb_profile_reset(nsb_handle h);
 int nsb_profile_get(nsb_handle h, const char* name, double* total_ms, int64_t* launches);
 /* what the last solve used: degree of the velocity polynomial, its residual reduction on the
  * probe vector, number of multigrid levels of K_p */
 int nsb_solver_info(nsb_handle h, int* poly_degree, double* poly_probe_residual, int* amg_levels);
+/* the packed velocity operator as stored: precision (16 / 32; 64 = none, the fp64 values are used), bytes of its value
+ * array, bytes of its index side (block metadata, tile headers, unique-neighbour lists), tiles, (node, neighbour) blocks */
+int nsb_velocity_operator_info(nsb_handle h, int* precision, int64_t* value_bytes, int64_t* index_bytes, int64_t* tiles,
+                               int64_t* blocks);
 /* how many kernels this library launched since nsb_create */
 int nsb_launch_count(nsb_handle h, int64_t* n);
 

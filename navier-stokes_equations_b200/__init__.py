@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NSB200_LIB", os.path.join(_HERE, "libnsb200.so"))   # override: kernel-variant experiments
 
 NSB_SOLUTION_OLD, NSB_SOLUTION_OLD_OLD, NSB_CURRENT_SOLUTION, NSB_SOLUTION, NSB_RHS = 0, 1, 2, 3, 4
-PROFILE_CLASSES = ("asm_context", "asm_rows", "spmv", "spmv_vel", "schur", "amg", "orth", "other")
+PROFILE_CLASSES = ("asm_context", "asm_rows", "spmv", "spmv_vel", "schur", "amg", "orth", "other", "asm_pack")
 
 
 class NsbError(RuntimeError):
@@ -247,6 +247,12 @@ class Device:
         d, r, l = C.c_int(), C.c_double(), C.c_int()
         self._ck(lib().nsb_solver_info(self.h, C.byref(d), C.byref(r), C.byref(l)))
         return dict(poly_degree=d.value, poly_probe_residual=r.value, amg_levels=l.value)
+
+    def velocity_operator_info(self):
+        p = C.c_int()
+        v = [C.c_int64() for _ in range(4)]
+        self._ck(lib().nsb_velocity_operator_info(self.h, C.byref(p), *[C.byref(x) for x in v]))
+        return dict(precision=p.value, value_bytes=v[0].value, index_bytes=v[1].value, tiles=v[2].value, blocks=v[3].value)
 
     def launch_count(self):
         n = C.c_int64()

@@ -374,8 +374,6 @@ struct RowOut {
   double* vals;            // CSR values of A (local rows, scalar-CSR order)
   double* rhs;             // [n_own]
   double* dinv;            // [nn_own][DIM*DIM]  inverse of the node-diagonal velocity block (preconditioner)
-  float* vals_f;           // optional fp32 copy of F, node-interleaved (see k_spmv_vel_f32), may be null
-  float* s_rows;           // optional: S_e[a][b] per (node, cell) pair at ebe_index(pair, b) (see ebe.cuh), may be null
 };
 
 template <int DIM, bool NEWTON>
@@ -561,10 +559,6 @@ k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double
 #pragma unroll
         for (int k = 0; k < DIM; ++k) trG += shfl_d(Gdd, grp + k);
         Sab = absJ * T.Mhat[a][b] * P.inv_dt + P.theta * P.nu * trG + Svar;
-      } else if (out.s_rows && act && d == 0) {
-        // row a of S_e for the element-wise velocity operator (ebe.cuh), blocked by 32 pairs
-        const long long p = kc0 + ic;
-        out.s_rows[((size_t)(p >> 5) * (NN / 2) + (size_t)(b >> 1)) * 64 + (size_t)(p & 31) * 2 + (size_t)(b & 1)] = (float)Sab;
       }
       double val[DIM];
 #pragma unroll
@@ -628,13 +622,6 @@ k_node_rows(DevMesh M, AsmParams P, const double* __restrict__ ctx, const double
         if (crow[c]) v = (k == selfk + c) ? dacc[c] : 0.0;
         acc[c * len + k] = v;
         out.vals[M.rowbase[A] + (long long)c * len + k] = v;
-      }
-      if (out.vals_f && k < DIM * nb) {
-        // fp32 copy of the velocity block, one vector per column holding all DIM rows
-        constexpr int W = (DIM == 3) ? 4 : 2;
-        float* o = out.vals_f + ((long long)DIM * nptr[0] + k) * W;
-        if (DIM == 3) *reinterpret_cast<float4*>(o) = make_float4((float)acc[k], (float)acc[len + k], (float)acc[2 * len + k], 0.f);
-        else *reinterpret_cast<float2*>(o) = make_float2((float)acc[k], (float)acc[len + k]);
       }
       if (isv) {
         double v = acc[DIM * len + k];

@@ -319,73 +319,6 @@ k_spmv_vel(DevMesh M, SpmvTiles TL, const VT* __restrict__ vals, const double* _
   }
 }
 
-// Same operator and epilogues as k_spmv_vel, reading the PRIVATE fp32 copy of F that the assembly
-// writes node-interleaved: for node A and column k < dim*nb one vector {F[(A,0),k], .., F[(A,dim-1),k](,0)}
-// at index dim*nbr0(A) + k.  One 16-byte (3-D) / 8-byte (2-D) load per lane and column delivers all rows,
-// three times fewer memory requests than the row-major fp64 layout and 2/3 of its bytes.  Products are
-// accumulated in fp64, so the preconditioner remains a fixed linear operator.
-template <int DIM> struct F32Vec { using type = float4; };
-template <> struct F32Vec<2> { using type = float2; };
-
-#ifndef NSB_F32_UNROLL
-#define NSB_F32_UNROLL 3
-#endif
-// storage of the staged x inside k_spmv_vel_f32: double keeps the operator exactly linear (staging x as float was
-// measured slower, see profiles/README.md)
-using F32X = double;
-constexpr int F32_UNROLL = NSB_F32_UNROLL;  // 3 x 32 columns covers the 81 columns of a line node in one trip
-
-// LISTED: the CTA's tile is tile_list[blockIdx.x] -- used by the multi-GPU path to run the tiles that read no
-// ghost entries while the halo exchange is in flight, and the boundary tiles afterwards.
-template <int DIM, int MODE, bool LISTED = false>
-__global__ void __launch_bounds__(SPMV_WARPS * 32)
-k_spmv_vel_f32(DevMesh M, SpmvTiles TL, const typename F32Vec<DIM>::type* __restrict__ fv,
-               const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ u,
-               double* __restrict__ poly, const double* __restrict__ dinv, PolyCoef pc,
-               const int* __restrict__ tile_list = nullptr) {
-  using V = typename F32Vec<DIM>::type;
-  __shared__ TileSmem<DIM, F32X> T;
-  const int lane = threadIdx.x & 31;
-  int n0, n1;
-  stage_tile<DIM, false, F32X>(M, TL, LISTED ? __ldg(tile_list + blockIdx.x) : (int)blockIdx.x, x, T, n0, n1);
-  for (;;) {
-    int slot = 0;
-    if (lane == 0) slot = atomicAdd(&T.next, 1);
-    slot = __shfl_sync(NSB_FULL, slot, 0);
-    const int A = n0 + slot;
-    if (A >= n1) break;
-    const NodeDesc d = desc_from_smem(T, slot);
-    const int nbd = DIM * d.nb;
-    EpiOps<DIM> eo;
-    vel_prefetch<DIM, MODE>(A, lane, u, poly, dinv, eo);
-    const V* rp = fv + (long long)DIM * d.nbr0;
-    const unsigned short* nx = T.idx + (d.nbr0 - T.base_n);
-    double sum[DIM];
-#pragma unroll
-    for (int c = 0; c < DIM; ++c) sum[c] = 0.0;
-    for (int k0 = 0; k0 < nbd; k0 += 32 * F32_UNROLL) {
-      V v[F32_UNROLL];
-      double xv[F32_UNROLL];
-#pragma unroll
-      for (int q = 0; q < F32_UNROLL; ++q) {
-        const int k = k0 + 32 * q + lane;
-        v[q] = V();
-        xv[q] = 0.0;
-        if (k < nbd) { v[q] = NSB_STREAM_LOAD(rp + k); xv[q] = (double)T.xs[(int)nx[k / DIM] * DIM + k % DIM]; }
-      }
-#pragma unroll
-      for (int q = 0; q < F32_UNROLL; ++q) {
-        sum[0] += (double)v[q].x * xv[q];
-        sum[1] += (double)v[q].y * xv[q];
-        if (DIM == 3) sum[DIM - 1] += (double)reinterpret_cast<const float*>(&v[q])[DIM - 1] * xv[q];
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < DIM; ++c) sum[c] = warp_sum_fixed(sum[c]);
-    vel_epilogue<DIM, MODE>(A, lane, sum, y, poly, eo, pc);
-  }
-}
-
 // t = g - B y0 : pressure rows, velocity columns (reference NavierStokes.hpp:334-335)
 template <int DIM, typename VT>
 __global__ void __launch_bounds__(SPMV_WARPS * 32)

@@ -21,8 +21,8 @@
 #include "assemble.cuh"
 #include "device.cuh"
 #include "linalg.cuh"
-#include "ebe.cuh"
 #include "structure.hpp"
+#include "velstream.cuh"
 
 using namespace nsb;
 
@@ -100,8 +100,8 @@ template <typename T> struct DBuf {
   }
 };
 
-enum ProfCat { PC_ASM_CTX = 0, PC_ASM_ROWS, PC_SPMV, PC_SPMV_VEL, PC_SCHUR, PC_AMG, PC_ORTH, PC_OTHER, PC_N };
-const char* kProfNames[PC_N] = {"asm_context", "asm_rows", "spmv", "spmv_vel", "schur", "amg", "orth", "other"};
+enum ProfCat { PC_ASM_CTX = 0, PC_ASM_ROWS, PC_SPMV, PC_SPMV_VEL, PC_SCHUR, PC_AMG, PC_ORTH, PC_OTHER, PC_ASM_PACK, PC_N };
+const char* kProfNames[PC_N] = {"asm_context", "asm_rows", "spmv", "spmv_vel", "schur", "amg", "orth", "other", "asm_pack"};
 
 struct Prof {
   bool on = false;
@@ -212,14 +212,12 @@ struct nsb_ctx {
   nsb_params par{};
   nsb_solver_opts opt{};
   DBuf<double> vals, dinv, ctx, cell_rhs;
-  DBuf<float> vals_f;               // fp32 copy of the values: operator of the velocity polynomial
-  // element-wise velocity operator (ebe.cuh): per-pair rows of S_e and tile-local node positions
-  DBuf<float> s_rows;
-  DBuf<unsigned short> d_pair_loc, d_pair_ca;
-  DBuf<int> d_tile_cell_ptr, d_tile_cells;
-  int ebe_smem_bytes = 0, ebe_ypair_doubles = 0;
-  bool ebe_valid = false;           // s_rows describe the currently assembled (linearised) system
-  double ebe_gamma = 0.0;
+  // streamed velocity operator (velstream.cuh): packed copy of Dinv F in fp32 / fp16, tile headers, block metadata
+  DBuf<unsigned char> vs_vals;
+  DBuf<VsTile> d_vs_tiles;
+  DBuf<uint32_t> d_vs_meta;
+  int64_t vs_total_nq = 0;
+  bool vs_valid = false;            // vs_vals describe the currently assembled system
   int ctx_stride = 0;
   // pressure matrices (global, replicated)
   HostCsr h_Mp, h_Kp;
@@ -274,15 +272,14 @@ int fail(nsb_ctx* c, const std::string& m, int code = -1) {
 
 inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 
-// operator used inside the velocity polynomial: 1 = assembled copy (fp32 / fp64), 2 = element-wise (ebe.cuh)
-#ifndef NSB_DEFAULT_PRECOND_OPERATOR
-#define NSB_DEFAULT_PRECOND_OPERATOR 1
+#ifndef NSB_DEFAULT_PRECOND_PRECISION
+#define NSB_DEFAULT_PRECOND_PRECISION 32
 #endif
 
-// the node-interleaved fp32 copy of F is only kept when the assembled operator runs in fp32
-size_t vals_f_size(const nsb_ctx* c) {
-  if (c->opt.precond_precision == 64 || c->opt.precond_operator == 2) return 0;
-  return (size_t)c->S.nbr.size() * c->dim * (c->dim == 3 ? 4 : 2);
+// bytes of the packed copy of Dinv F (none when the polynomial runs on the fp64 values themselves)
+size_t vs_vals_bytes(const nsb_ctx* c) {
+  if (c->opt.precond_precision == 64) return 0;
+  return (size_t)c->vs_total_nq * 4 * c->dim * c->dim * (c->opt.precond_precision == 16 ? 2 : 4);
 }
 
 // ---- halo exchange of one local vector (ghost tail refreshed from the owners) -----------
@@ -377,9 +374,7 @@ template <int DIM> void launch_assemble(nsb_ctx* c, bool newton) {
     k_cell_context<DIM, false><<<cgrid, ASM_WARPS * 32, 0, c->stream>>>(c->M, P, c->d_fe.p, vecA, vecB, c->ctx.p, c->cell_rhs.p);
   c->launch_check();
   c->prof.end(id, c->stream);
-  RowOut out{c->vals.p, c->v_rhs.p, c->dinv.p, c->vals_f.p, newton ? nullptr : c->s_rows.p};
-  c->ebe_valid = !newton && c->s_rows.p != nullptr;
-  c->ebe_gamma = P.gamma;
+  RowOut out{c->vals.p, c->v_rhs.p, c->dinv.p};
   id = c->prof.begin(PC_ASM_ROWS, c->stream);
   if (newton)
     k_node_rows<DIM, true><<<c->n_tiles, ASM_WARPS * 32, c->tile_smem_bytes, c->stream>>>(c->M, P, c->ctx.p, c->cell_rhs.p, c->cflag.p, c->cval.p, out, c->d_tile_ptr.p, c->d_fe.p);
@@ -387,6 +382,18 @@ template <int DIM> void launch_assemble(nsb_ctx* c, bool newton) {
     k_node_rows<DIM, false><<<c->n_tiles, ASM_WARPS * 32, c->tile_smem_bytes, c->stream>>>(c->M, P, c->ctx.p, c->cell_rhs.p, c->cflag.p, c->cval.p, out, c->d_tile_ptr.p, c->d_fe.p);
   c->launch_check();
   c->prof.end(id, c->stream);
+  // packed copy of Dinv F for the streamed velocity operator
+  c->vs_valid = false;
+  if (c->vs_vals.p) {
+    id = c->prof.begin(PC_ASM_PACK, c->stream);
+    if (c->opt.precond_precision == 16)
+      k_vel_pack<DIM, __half><<<c->n_stiles, 256, 0, c->stream>>>(c->M, c->d_vs_tiles.p, c->d_vs_meta.p, c->vals.p, c->dinv.p, reinterpret_cast<__half*>(c->vs_vals.p));
+    else
+      k_vel_pack<DIM, float><<<c->n_stiles, 256, 0, c->stream>>>(c->M, c->d_vs_tiles.p, c->d_vs_meta.p, c->vals.p, c->dinv.p, reinterpret_cast<float*>(c->vs_vals.p));
+    c->launch_check();
+    c->prof.end(id, c->stream);
+    c->vs_valid = true;
+  }
 }
 
 template <int DIM> void set_smem_attr(int bytes) {
@@ -394,9 +401,32 @@ template <int DIM> void set_smem_attr(int bytes) {
   CK(cudaFuncSetAttribute(k_node_rows<DIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 }
 
-template <int DIM> void set_ebe_attr(int bytes) {
-  CK(cudaFuncSetAttribute(k_apply_F_ebe<DIM, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CK(cudaFuncSetAttribute(k_apply_F_ebe<DIM, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+template <int DIM, typename VT> void set_vs_attr() {
+  const int bytes = VsLayout<DIM, VT>::SMEM_BYTES;
+  CK(cudaFuncSetAttribute(k_vel_stream<DIM, VT, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CK(cudaFuncSetAttribute(k_vel_stream<DIM, VT, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CK(cudaFuncSetAttribute(k_vel_stream<DIM, VT, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+}
+
+// one application of the streamed operator over `ntiles` tiles (all of them, or the listed ones)
+template <int DIM, typename VT, int MODE, bool LISTED>
+void launch_vel_stream(nsb_ctx* c, int ntiles, const int* list, const double* x, double* y, const double* u, double* poly, PolyCoef pc) {
+  if (ntiles <= 0) return;
+  const int grid = std::min(ntiles, c->num_sms);
+  k_vel_stream<DIM, VT, MODE, LISTED><<<grid, VS_THREADS, VsLayout<DIM, VT>::SMEM_BYTES, c->stream>>>(
+      c->d_vs_tiles.p, ntiles, list, reinterpret_cast<const VT*>(c->vs_vals.p), c->d_vs_meta.p, c->d_suniq_xoff.p, x, y, u, poly, pc);
+  c->launch_check();
+}
+template <int MODE, bool LISTED>
+void vel_stream(nsb_ctx* c, int ntiles, const int* list, const double* x, double* y, const double* u, double* poly, PolyCoef pc) {
+  const bool h = c->opt.precond_precision == 16;
+  if (c->dim == 2) {
+    if (h) launch_vel_stream<2, __half, MODE, LISTED>(c, ntiles, list, x, y, u, poly, pc);
+    else launch_vel_stream<2, float, MODE, LISTED>(c, ntiles, list, x, y, u, poly, pc);
+  } else {
+    if (h) launch_vel_stream<3, __half, MODE, LISTED>(c, ntiles, list, x, y, u, poly, pc);
+    else launch_vel_stream<3, float, MODE, LISTED>(c, ntiles, list, x, y, u, poly, pc);
+  }
 }
 
 // y(owned) = A x ; x must have a valid ghost tail
@@ -412,26 +442,20 @@ template <int MODE>
 void spmv_vel(nsb_ctx* c, const double* x, double* y, const double* u, double* poly, PolyCoef pc) {
   size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
   const int g = c->n_stiles;
-  if (c->ebe_valid && MODE != 0) {
-    const EbeData E{c->s_rows.p, c->d_pair_loc.p, c->d_pair_ca.p, c->d_tile_cell_ptr.p, c->d_tile_cells.p, c->cflag.p, c->ebe_gamma,
-                    c->ebe_ypair_doubles};
-    if (c->dim == 2) k_apply_F_ebe<2, MODE><<<g, EBE_THREADS, c->ebe_smem_bytes, c->stream>>>(c->M, c->stiles, E, c->d_fe.p, x, y, u, poly, c->dinv.p, pc);
-    else k_apply_F_ebe<3, MODE><<<g, EBE_THREADS, c->ebe_smem_bytes, c->stream>>>(c->M, c->stiles, E, c->d_fe.p, x, y, u, poly, c->dinv.p, pc);
-  } else if (c->vals_f.p && MODE != 0) {
-    if (c->dim == 2) k_spmv_vel_f32<2, MODE><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float2*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
-    else k_spmv_vel_f32<3, MODE><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float4*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc);
+  if (c->vs_valid && MODE != 0) {
+    vel_stream<MODE == 0 ? 2 : MODE, false>(c, g, nullptr, x, y, u, poly, pc);
   } else {
     if (c->dim == 2) k_spmv_vel<2, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, c->vals.p, x, y, u, poly, c->dinv.p, pc);
     else k_spmv_vel<3, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, c->vals.p, x, y, u, poly, c->dinv.p, pc);
+    c->launch_check();
   }
-  c->launch_check();
   c->prof.end(id, c->stream);
 }
 
-// one root of the velocity polynomial on a vector whose ghosts are stale: exchange + F application, overlapped when
-// the fp32 assembled operator is in use on several GPUs
+// one root of the velocity polynomial on a vector whose ghosts are stale: exchange + operator application; with
+// NSB200_OVERLAP=1 the tiles that read no ghost entry run while the exchange is in flight, the boundary tiles after it
 void halo_spmv_vel3(nsb_ctx* c, double* x, double* y, const double* u, double* poly, PolyCoef pc) {
-  const bool ovl = c->nranks > 1 && c->overlap && c->vals_f.p && !c->ebe_valid && c->n_tiles_int > 0;
+  const bool ovl = c->nranks > 1 && c->overlap && c->vs_valid && c->n_tiles_int > 0;
   if (!ovl) {
     halo_exchange(c, x, false);
     spmv_vel<3>(c, x, y, u, poly, pc);
@@ -439,15 +463,9 @@ void halo_spmv_vel3(nsb_ctx* c, double* x, double* y, const double* u, double* p
   }
   halo_start_velocity(c, x);
   size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
-  if (c->dim == 2) k_spmv_vel_f32<2, 3, true><<<c->n_tiles_int, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float2*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc, c->d_tiles_int.p);
-  else k_spmv_vel_f32<3, 3, true><<<c->n_tiles_int, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float4*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc, c->d_tiles_int.p);
-  c->launch_check();
+  vel_stream<3, true>(c, c->n_tiles_int, c->d_tiles_int.p, x, y, u, poly, pc);
   CK(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
-  if (c->n_tiles_bnd > 0) {
-    if (c->dim == 2) k_spmv_vel_f32<2, 3, true><<<c->n_tiles_bnd, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float2*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc, c->d_tiles_bnd.p);
-    else k_spmv_vel_f32<3, 3, true><<<c->n_tiles_bnd, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, reinterpret_cast<const float4*>(c->vals_f.p), x, y, u, poly, c->dinv.p, pc, c->d_tiles_bnd.p);
-    c->launch_check();
-  }
+  vel_stream<3, true>(c, c->n_tiles_bnd, c->d_tiles_bnd.p, x, y, u, poly, pc);
   c->prof.end(id, c->stream);
 }
 
@@ -909,47 +927,36 @@ void build_tiles(nsb_ctx* c) {
   c->n_tiles = (int)tp.size() - 1;
   c->tile_smem_bytes = budget * 8;
   c->d_tile_ptr.upload(tp, c->stream);
-  // SpMV tiles (plan built and checked on the host: structure.cpp build_tile_plan / verify_tile_plan)
+  // SpMV tiles (plan built and checked on the host: structure.cpp build_tile_plan / verify_tile_plan) and the streamed
+  // velocity operator's headers / metadata on top of them (build_vel_stream)
   {
     TilePlan P;
-    const TileLimits L{TILE_MAX_NODES, TILE_MAX_IDX, TILE_MAX_UNIQ, TILE_MAX_PUNIQ};
-    const std::string err = build_tile_plan(S, L, c->opt.precond_operator == 2, P);
+    const TileLimits L{TILE_MAX_NODES, TILE_MAX_IDX, TILE_MAX_UNIQ, TILE_MAX_PUNIQ, VS_MAX_BLOCKS};
+    const std::string err = build_tile_plan(S, L, P);
     if (!err.empty()) throw CudaErr{err};
+    VsPlan V;
+    const std::string err2 = build_vel_stream(S, P, V);
+    if (!err2.empty()) throw CudaErr{err2};
     c->n_stiles = P.n_tiles();
-    c->ebe_ypair_doubles = P.max_pairs * S.dim;
-    c->ebe_smem_bytes = 0;
-    if (c->opt.precond_operator == 2) {
-      c->ebe_smem_bytes = (c->ebe_ypair_doubles + P.max_ucells * ((S.dim + 1) * S.dim + 1)) * (int)sizeof(double);
-      c->d_pair_loc.upload(P.pair_loc, c->stream);
-      c->d_pair_ca.upload(P.pair_ca, c->stream);
-      c->d_tile_cell_ptr.upload(P.tile_cell_ptr, c->stream);
-      c->d_tile_cells.upload(P.tile_cells, c->stream);
-      c->s_rows.alloc(P.pair_loc.size());
-      CK(cudaMemsetAsync(c->s_rows.p, 0, P.pair_loc.size() * sizeof(float), c->stream));
-    } else {
-      c->d_pair_loc.alloc(0); c->d_pair_ca.alloc(0);
-      c->d_tile_cell_ptr.alloc(0); c->d_tile_cells.alloc(0);
-      c->s_rows.alloc(0);
-    }
-    c->ebe_valid = false;
     c->d_stile_ptr.upload(P.node_ptr, c->stream);
     c->n_tiles_int = (int)P.tiles_int.size(); c->n_tiles_bnd = (int)P.tiles_bnd.size();
     c->d_tiles_int.upload(P.tiles_int, c->stream); c->d_tiles_bnd.upload(P.tiles_bnd, c->stream);
     c->d_suniq_ptr.upload(P.uniq_ptr, c->stream); c->d_suniq_xoff.upload(P.uniq_xoff, c->stream);
     c->d_spuniq_ptr.upload(P.puniq_ptr, c->stream); c->d_spuniq_xoff.upload(P.puniq_xoff, c->stream);
     c->d_nbr_loc.upload(P.nbr_loc, c->stream); c->d_pnbr_loc.upload(P.pnbr_loc, c->stream);
-    CK(cudaStreamSynchronize(c->stream));       // the plan's host vectors die with this scope
+    c->d_vs_tiles.upload(V.tiles, c->stream); c->d_vs_meta.upload(V.meta, c->stream);
+    c->vs_total_nq = V.total_nq;
+    CK(cudaStreamSynchronize(c->stream));       // the plans' host vectors die with this scope
     c->stiles.node_ptr = c->d_stile_ptr.p;
     c->stiles.uniq_ptr = c->d_suniq_ptr.p; c->stiles.uniq_xoff = c->d_suniq_xoff.p;
     c->stiles.puniq_ptr = c->d_spuniq_ptr.p; c->stiles.puniq_xoff = c->d_spuniq_xoff.p;
     c->stiles.nbr_loc = c->d_nbr_loc.p; c->stiles.pnbr_loc = c->d_pnbr_loc.p;
   }
+  c->vs_vals.alloc(vs_vals_bytes(c));
+  c->vs_valid = false;
   CK(cudaStreamSynchronize(c->stream));
-  if (c->dim == 2) set_smem_attr<2>(c->tile_smem_bytes);
-  else set_smem_attr<3>(c->tile_smem_bytes);
-  if (c->ebe_smem_bytes + 28 * 1024 > dev_max) throw CudaErr{"the pair results of one SpMV tile do not fit in shared memory"};
-  if (c->dim == 2) set_ebe_attr<2>(c->ebe_smem_bytes);
-  else set_ebe_attr<3>(c->ebe_smem_bytes);
+  if (c->dim == 2) { set_smem_attr<2>(c->tile_smem_bytes); set_vs_attr<2, float>(); set_vs_attr<2, __half>(); }
+  else { set_smem_attr<3>(c->tile_smem_bytes); set_vs_attr<3, float>(); set_vs_attr<3, __half>(); }
 }
 
 // one-time M_p, K_p on the host over the GLOBAL P1 graph (reference cpp:798-803, 812-829)
@@ -1075,8 +1082,9 @@ int nsb_create(int dim, int device, nsb_handle* out) {
   }
   CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   c->opt.poly_degree_F = 64; c->opt.poly_refresh = 1; c->opt.poly_target = 0.08; c->opt.poly_kind = 1; c->opt.cheb_degree_Mp = 3;
-  c->opt.amg_smoother_degree = 2; c->opt.schur_mass_coeff = -1.0; c->opt.reorthogonalize = 1; c->opt.precond_precision = 32;
-  c->opt.precond_operator = NSB_DEFAULT_PRECOND_OPERATOR;
+  c->opt.amg_smoother_degree = 2; c->opt.schur_mass_coeff = -1.0; c->opt.reorthogonalize = 1;
+  c->opt.precond_precision = NSB_DEFAULT_PRECOND_PRECISION;
+  c->opt.precond_operator = 1;
   c->par.dt = 0.01; c->par.theta = 1.0; c->par.nu = 1e-3; c->par.rho = 1.0; c->par.gamma = 0.1;
   c->d_nrm.alloc(4);
   return 0;
@@ -1236,7 +1244,6 @@ int nsb_upload_mesh(nsb_handle c, int64_t n_vertices, const double* coords, int6
   CK(cudaMallocHost(&c->pin, nt * sizeof(double)));
   c->cflag.alloc(nt); c->cflag.zero(st);
   c->vals.alloc((size_t)S.nnz_local);
-  c->vals_f.alloc(vals_f_size(c));
   c->dinv.alloc((size_t)S.nn_own * dim * dim);
   c->cell_rhs.alloc((size_t)S.nc * S.DPC);
   c->ctx_stride = 0;
@@ -1345,16 +1352,16 @@ int nsb_set_solver_opts(nsb_handle c, const nsb_solver_opts* o) {
   if (n.amg_smoother_degree <= 0) n.amg_smoother_degree = 2;
   if (n.schur_mass_coeff == 0.0) n.schur_mass_coeff = -1.0;
   if (n.reorthogonalize == 0) n.reorthogonalize = 1;   // 0 = default (twice); negative = a single pass
-  if (n.precond_precision != 64) n.precond_precision = 32;
-  if (n.precond_operator != 1 && n.precond_operator != 2) n.precond_operator = NSB_DEFAULT_PRECOND_OPERATOR;
-  const bool changed = n.precond_precision != c->opt.precond_precision || n.precond_operator != c->opt.precond_operator;
+  if (n.precond_precision != 64 && n.precond_precision != 16 && n.precond_precision != 32) n.precond_precision = NSB_DEFAULT_PRECOND_PRECISION;
+  n.precond_operator = 1;                         // the element-wise operator of round 1 is gone (slower than the packed copy)
+  const bool changed = n.precond_precision != c->opt.precond_precision;
   c->opt = n;
   if (c->have_mesh && changed) {
-    // (de)allocate the operator copies of the velocity polynomial; they are refilled by the next assembly
+    // (de)allocate the packed operator copy of the velocity polynomial; it is refilled by the next assembly
     try {
       cudaSetDevice(c->device);
-      c->vals_f.alloc(vals_f_size(c));
-      build_tiles(c);
+      c->vs_vals.alloc(vs_vals_bytes(c));
+      c->vs_valid = false;
     } catch (const CudaErr& e) { return fail(c, e.msg); }
     c->have_matrix = false;
     c->poly_roots.clear();
@@ -1727,21 +1734,24 @@ int nsb_test_halo_plan(int dim, int64_t n_vertices, const double* coords, int64_
 }
 
 /* eigenvalues of an upper-Hessenberg matrix */
-// host-only: builds rank's structure and SpMV tile plan (optionally with the element-wise arrays) and checks every
-// invariant the kernels rely on; out = {tiles, interior tiles, boundary tiles, max pairs per tile, violations}
+// host-only: builds rank's structure, its SpMV tile plan and the streamed-operator plan on top of it and checks every
+// invariant the kernels rely on; out = {tiles, interior tiles, boundary tiles, padded velocity blocks, violations}
 int nsb_test_tile_plan(int dim, int64_t n_vertices, const double* coords, int64_t n_cells, const uint32_t* cell_vertices,
                        const uint32_t* cell_dofs, int64_t n_u, int64_t n_p, const int32_t* cell_part, int rank, int nranks,
-                       int with_elementwise, int64_t* out5) {
+                       int64_t* out5) {
   Structure S;
   const std::string e = build_structure(dim, n_vertices, coords, n_cells, cell_vertices, cell_dofs, n_u, n_p,
                                         nranks > 1 ? cell_part : nullptr, rank, nranks, S);
   if (!e.empty()) { std::fprintf(stderr, "nsb_test_tile_plan: %s\n", e.c_str()); return -1; }
   TilePlan P;
-  const TileLimits L{TILE_MAX_NODES, TILE_MAX_IDX, TILE_MAX_UNIQ, TILE_MAX_PUNIQ};
-  const std::string e2 = build_tile_plan(S, L, with_elementwise != 0, P);
+  const TileLimits L{TILE_MAX_NODES, TILE_MAX_IDX, TILE_MAX_UNIQ, TILE_MAX_PUNIQ, VS_MAX_BLOCKS};
+  const std::string e2 = build_tile_plan(S, L, P);
   if (!e2.empty()) { std::fprintf(stderr, "nsb_test_tile_plan: %s\n", e2.c_str()); return -1; }
+  VsPlan V;
+  const std::string e3 = build_vel_stream(S, P, V);
+  if (!e3.empty()) { std::fprintf(stderr, "nsb_test_tile_plan: %s\n", e3.c_str()); return -1; }
   out5[0] = P.n_tiles(); out5[1] = (int64_t)P.tiles_int.size(); out5[2] = (int64_t)P.tiles_bnd.size();
-  out5[3] = P.max_pairs; out5[4] = verify_tile_plan(S, L, P);
+  out5[3] = 4 * V.total_nq; out5[4] = verify_tile_plan(S, L, P) + verify_vel_stream(S, P, V);
   return 0;
 }
 
@@ -1762,6 +1772,17 @@ int nsb_solver_info(nsb_handle c, int* poly_degree, double* poly_probe_residual,
   }
   if (poly_probe_residual) *poly_probe_residual = c->poly_probe_res;
   if (amg_levels) *amg_levels = (int)c->amg.size();
+  return 0;
+}
+
+int nsb_velocity_operator_info(nsb_handle c, int* precision, int64_t* value_bytes, int64_t* index_bytes, int64_t* tiles,
+                               int64_t* blocks) {
+  if (!c || !c->have_mesh) return fail(c, "no mesh uploaded");
+  if (precision) *precision = c->opt.precond_precision;
+  if (value_bytes) *value_bytes = (int64_t)vs_vals_bytes(c);
+  if (index_bytes) *index_bytes = 16 * c->vs_total_nq + 64 * (int64_t)c->n_stiles + 4 * (int64_t)c->d_suniq_xoff.n;
+  if (tiles) *tiles = c->n_stiles;
+  if (blocks) *blocks = (int64_t)c->S.nbr.size();
   return 0;
 }
 

@@ -2,6 +2,7 @@
 #include "structure.hpp"
 
 #include <algorithm>
+#include <cstring>
 #include <climits>
 #include <cmath>
 #include <numeric>
@@ -394,7 +395,7 @@ void export_row_gids(const Structure& S, std::vector<int64_t>& gid) {
   for (int P = 0; P < S.np_own; ++P) gid[(int64_t)S.dim * S.nn_own + P] = S.n_u_glob + S.pid_gid[P];
 }
 
-std::string build_tile_plan(const Structure& S, const TileLimits& L, bool with_elementwise, TilePlan& P) {
+std::string build_tile_plan(const Structure& S, const TileLimits& L, TilePlan& P) {
   P = TilePlan();
   const int ntot = S.nn_own + S.nn_ghost, ptot = S.np_own + S.np_ghost;
   P.nbr_loc.assign(S.nbr.size(), 0);
@@ -405,13 +406,15 @@ std::string build_tile_plan(const Structure& S, const TileLimits& L, bool with_e
   std::vector<int> U, PU;
   while (A < S.nn_own) {
     U.clear(); PU.clear();
-    int idx = 0, cn = 0;
+    int idx = 0, cn = 0, vblk = 0;
     const int start = A;
     while (A < S.nn_own && cn < L.max_nodes) {
       const int nb = (int)(S.nbr_ptr[A + 1] - S.nbr_ptr[A]), np = (int)(S.pnbr_ptr[A + 1] - S.pnbr_ptr[A]);
-      if (nb + np > L.max_idx || nb > L.max_uniq || np > L.max_puniq)
+      if (nb + np > L.max_idx || nb > L.max_uniq || np > L.max_puniq || (L.max_vel_blocks && (nb + 3) / 4 * 4 > L.max_vel_blocks))
         return "a node has more neighbours than one SpMV tile can stage";
       if (idx + nb + np > L.max_idx) break;
+      if (L.max_vel_blocks && vblk + (nb + 3) / 4 * 4 > L.max_vel_blocks) break;      // blocks padded to quads
+      vblk += (nb + 3) / 4 * 4;
       int newu = 0, newp = 0;
       for (int64_t k = S.nbr_ptr[A]; k < S.nbr_ptr[A + 1]; ++k) newu += stamp[S.nbr[k]] != tile;
       for (int64_t k = S.pnbr_ptr[A]; k < S.pnbr_ptr[A + 1]; ++k) newp += pstamp[S.pnbr[k]] != tile;
@@ -437,43 +440,101 @@ std::string build_tile_plan(const Structure& S, const TileLimits& L, bool with_e
     P.node_ptr.push_back(A); P.uniq_ptr.push_back((int)P.uniq_xoff.size()); P.puniq_ptr.push_back((int)P.puniq_xoff.size());
     ++tile;
   }
-  const auto& sp = P.node_ptr;
-  for (size_t t = 0; t + 1 < sp.size(); ++t)
-    P.max_pairs = std::max(P.max_pairs, (int)(S.n2c_ptr[sp[t + 1]] - S.n2c_ptr[sp[t]]));
-  if (!with_elementwise) return "";
-  // element-wise velocity operator: tile-local position of every cell node of every (node, cell) pair, blocked by
-  // 32 pairs like the S rows the assembly writes (ebe.cuh)
-  const int NN = S.NN;
-  const int64_t NP = (int64_t)S.n2c.size();
-  P.pair_loc.assign((size_t)((NP + 31) / 32) * 32 * NN, 0);
-  P.pair_ca.assign((size_t)NP, 0);
+  return "";
+}
+
+std::string build_vel_stream(const Structure& S, const TilePlan& P, VsPlan& V) {
+  V = VsPlan();
+  const int nt = P.n_tiles();
+  V.tiles.resize(nt);
+  auto quads = [&](int A) { return (int)((S.nbr_ptr[A + 1] - S.nbr_ptr[A] + 3) / 4); };
+  int64_t off = 0;
+  std::vector<int> qstart;
+  for (int t = 0; t < nt; ++t) {
+    VsTile& T = V.tiles[t];
+    std::memset(&T, 0, sizeof(T));
+    T.n0 = P.node_ptr[t]; T.nn = P.node_ptr[t + 1] - T.n0;
+    qstart.assign(T.nn + 1, 0);
+    for (int a = 0; a < T.nn; ++a) qstart[a + 1] = qstart[a] + quads(T.n0 + a);
+    if (qstart[T.nn] > VS_MAX_QUADS) return "an SpMV tile holds more velocity blocks than the streamed operator can stage";
+    T.nquad = qstart[T.nn];
+    T.NQ = (T.nquad + 31) / 32 * 32;
+    if ((off + T.NQ) * 4 >= (int64_t)INT32_MAX) return "too many velocity blocks for 32-bit tile offsets";
+    T.nq_off = (int)off;
+    T.u0 = P.uniq_ptr[t]; T.nuq = P.uniq_ptr[t + 1] - T.u0;
+    // node-aligned split of the quads among the consumer warps, balanced by quad count
+    int a = 0;
+    for (int w = 0; w <= VS_CONSUMERS; ++w) {
+      const int target = (int)((int64_t)T.nquad * w / VS_CONSUMERS);
+      while (a < T.nn && qstart[a] < target) ++a;
+      T.split[w] = (unsigned short)qstart[a];
+    }
+    T.split[VS_CONSUMERS] = (unsigned short)T.nquad;
+    off += T.NQ;
+  }
+  V.total_nq = off;
+  V.meta.assign((size_t)off * 4, 0u);
 #pragma omp parallel for schedule(static)
-  for (int B = 0; B < S.nn_own; ++B)
-    for (int64_t k = S.n2c_ptr[B]; k < S.n2c_ptr[B + 1]; ++k) {
-      const uint32_t pk = S.n2c[k];
-      const size_t cell = pk >> 4, a = pk & 15u;
-      for (int b = 0; b < NN; ++b) {
-        const int rk = S.rank_uu[(cell * NN + a) * NN + b];
-        P.pair_loc[ebe_pair_index(NN, k, b)] = P.nbr_loc[S.nbr_ptr[B] + rk];
+  for (int t = 0; t < nt; ++t) {
+    const VsTile& T = V.tiles[t];
+    uint32_t* m = V.meta.data() + (size_t)T.nq_off * 4;
+    int q = 0;
+    for (int a = 0; a < T.nn; ++a) {
+      const int64_t k0 = S.nbr_ptr[T.n0 + a], k1 = S.nbr_ptr[T.n0 + a + 1];
+      for (int64_t k = k0; k < k1; k += 4, ++q) {
+        uint32_t loc[4];
+        const int cnt = (int)std::min<int64_t>(4, k1 - k);
+        for (int e = 0; e < 4; ++e) loc[e] = P.nbr_loc[k + (e < cnt ? e : 0)];      // padding blocks: a valid position, zero values
+        m[4 * q + 0] = loc[0] | (loc[1] << 16);
+        m[4 * q + 1] = loc[2] | (loc[3] << 16);
+        m[4 * q + 2] = (uint32_t)a;
+        m[4 * q + 3] = (uint32_t)(k - k0) | ((uint32_t)cnt << 16);
       }
     }
-  // unique cells per tile (ascending) and the pair's position in that list
-  std::vector<int> cpos(S.nc, 0), uc;
-  P.tile_cell_ptr.assign(1, 0);
-  for (size_t t = 0; t + 1 < sp.size(); ++t) {
-    uc.clear();
-    for (int64_t k = S.n2c_ptr[sp[t]]; k < S.n2c_ptr[sp[t + 1]]; ++k) uc.push_back((int)(S.n2c[k] >> 4));
-    std::sort(uc.begin(), uc.end());
-    uc.erase(std::unique(uc.begin(), uc.end()), uc.end());
-    if (uc.size() > 4096) return "an SpMV tile touches more than 4096 cells";
-    for (size_t i = 0; i < uc.size(); ++i) cpos[uc[i]] = (int)i;
-    for (int64_t k = S.n2c_ptr[sp[t]]; k < S.n2c_ptr[sp[t + 1]]; ++k)
-      P.pair_ca[k] = (unsigned short)((cpos[S.n2c[k] >> 4] << 4) | (S.n2c[k] & 15u));
-    P.tile_cells.insert(P.tile_cells.end(), uc.begin(), uc.end());
-    P.tile_cell_ptr.push_back((int)P.tile_cells.size());
-    P.max_ucells = std::max(P.max_ucells, (int)uc.size());
+    for (; q < T.NQ; ++q) { m[4 * q + 0] = 0; m[4 * q + 1] = 0; m[4 * q + 2] = 0xffffu; m[4 * q + 3] = 0; }
   }
   return "";
+}
+
+int64_t verify_vel_stream(const Structure& S, const TilePlan& P, const VsPlan& V) {
+  int64_t bad = 0;
+  const int nt = P.n_tiles();
+  if ((int)V.tiles.size() != nt) return 1;
+  int64_t off = 0;
+  int next_node = 0;
+  for (int t = 0; t < nt; ++t) {
+    const VsTile& T = V.tiles[t];
+    if (T.n0 != next_node || T.nn <= 0 || T.nn > 64) ++bad;
+    next_node = T.n0 + T.nn;
+    if (T.nq_off != off || T.NQ % 32 || T.NQ < T.nquad || T.NQ > VS_MAX_QUADS) ++bad;
+    if (T.u0 != P.uniq_ptr[t] || T.nuq != P.uniq_ptr[t + 1] - P.uniq_ptr[t]) ++bad;
+    const uint32_t* m = V.meta.data() + (size_t)off * 4;
+    int q = 0;
+    std::vector<int> qstart(1, 0);
+    for (int a = 0; a < T.nn; ++a) {
+      const int64_t k0 = S.nbr_ptr[T.n0 + a], k1 = S.nbr_ptr[T.n0 + a + 1];
+      for (int64_t k = k0; k < k1; k += 4, ++q) {
+        const int cnt = (int)(m[4 * q + 3] >> 16), first = (int)(m[4 * q + 3] & 0xffffu);
+        if ((int)m[4 * q + 2] != a || first != (int)(k - k0) || cnt != (int)std::min<int64_t>(4, k1 - k)) ++bad;
+        for (int e = 0; e < 4; ++e) {
+          const int loc = (int)((m[4 * q + e / 2] >> (16 * (e & 1))) & 0xffffu);
+          if (loc >= T.nuq) { ++bad; continue; }
+          if (e < cnt && P.uniq_xoff[T.u0 + loc] != (int)S.node_xoff(S.nbr[k + e])) ++bad;
+        }
+      }
+      qstart.push_back(q);
+    }
+    if (q != T.nquad) ++bad;
+    for (; q < T.NQ; ++q) if (m[4 * q + 2] != 0xffffu) ++bad;
+    if (T.split[0] != 0 || T.split[VS_CONSUMERS] != T.nquad) ++bad;
+    for (int w = 0; w < VS_CONSUMERS; ++w) {
+      if (T.split[w] > T.split[w + 1]) ++bad;
+      if (!std::binary_search(qstart.begin(), qstart.end(), (int)T.split[w])) ++bad;      // node-aligned
+    }
+    off += T.NQ;
+  }
+  if (next_node != S.nn_own || off != V.total_nq) ++bad;
+  return bad;
 }
 
 int64_t verify_tile_plan(const Structure& S, const TileLimits& L, const TilePlan& P) {
@@ -486,7 +547,6 @@ int64_t verify_tile_plan(const Structure& S, const TileLimits& L, const TilePlan
   for (int t : P.tiles_bnd) { if (t < 0 || t >= nt || seen[t]) ++bad; else seen[t] = 2; }
   for (int t = 0; t < nt; ++t) if (!seen[t]) ++bad;
   if (bad) return bad;
-  const bool ebe = !P.tile_cell_ptr.empty();
   for (int t = 0; t < nt; ++t) {
     const int n0 = P.node_ptr[t], n1 = P.node_ptr[t + 1];
     const int u0 = P.uniq_ptr[t], nu = P.uniq_ptr[t + 1] - u0, q0 = P.puniq_ptr[t], nq = P.puniq_ptr[t + 1] - q0;
@@ -509,24 +569,6 @@ int64_t verify_tile_plan(const Structure& S, const TileLimits& L, const TilePlan
       }
     }
     if (idx > L.max_idx) ++bad;
-    const int64_t p0 = S.n2c_ptr[n0], p1 = S.n2c_ptr[n1];
-    if (p1 - p0 > P.max_pairs) ++bad;
-    if (!ebe) continue;
-    const int c0 = P.tile_cell_ptr[t], nc = P.tile_cell_ptr[t + 1] - c0;
-    if (nc > P.max_ucells || nc > 4096) ++bad;
-    for (int i = 1; i < nc; ++i) if (P.tile_cells[c0 + i] <= P.tile_cells[c0 + i - 1]) ++bad;
-    for (int A = n0; A < n1; ++A)
-      for (int64_t k = S.n2c_ptr[A]; k < S.n2c_ptr[A + 1]; ++k) {
-        const int cell = (int)(S.n2c[k] >> 4), a = (int)(S.n2c[k] & 15u);
-        const int ca = P.pair_ca[k];
-        if ((ca & 15) != a || (ca >> 4) >= nc || P.tile_cells[c0 + (ca >> 4)] != cell) ++bad;
-        if (S.cell_nodes[(size_t)cell * S.NN + a] != A) ++bad;
-        for (int b = 0; b < S.NN; ++b) {
-          const int loc = P.pair_loc[ebe_pair_index(S.NN, k, b)];
-          const int node = S.cell_nodes[(size_t)cell * S.NN + b];
-          if (loc >= nu || P.uniq_xoff[u0 + loc] != (int)S.node_xoff(node)) ++bad;
-        }
-      }
   }
   return bad;
 }

@@ -73,12 +73,13 @@ std::string build_structure(int dim, int64_t n_vertices, const double* coords, i
                             const uint32_t* cell_vertices, const uint32_t* cell_dofs, int64_t n_u,
                             int64_t n_p, const int32_t* cell_part, int rank, int nranks, Structure& S);
 
-// Plan of the SpMV tiles (linalg.cuh / ebe.cuh): runs of consecutive owned nodes with bounded staged index count
+// Plan of the SpMV tiles (linalg.cuh / velstream.cuh): runs of consecutive owned nodes with bounded staged index count
 // and bounded UNIQUE neighbour sets; every neighbour reference rewritten as a 16-bit position in its tile's unique
-// list; tiles that read no ghost entry listed apart (halo / compute overlap); optionally the per-pair arrays of the
-// element-wise velocity operator.  Pure host logic, checked by verify_tile_plan() in the CPU tests.
+// list; tiles that read no ghost entry listed apart (halo / compute overlap).  Pure host logic, checked by
+// verify_tile_plan() in the CPU tests.
 struct TileLimits {
   int max_nodes, max_idx, max_uniq, max_puniq;
+  int max_vel_blocks = 0;                  // bound on the velocity blocks (node, neighbour node) of one tile; 0 = none
 };
 struct TilePlan {
   std::vector<int> node_ptr;               // [n_tiles+1]
@@ -87,22 +88,42 @@ struct TilePlan {
   std::vector<unsigned short> nbr_loc;     // parallel to Structure::nbr
   std::vector<unsigned short> pnbr_loc;    // parallel to Structure::pnbr
   std::vector<int> tiles_int, tiles_bnd;   // tiles without / with ghost neighbours
-  int max_pairs = 0;                       // most (node, cell) pairs in one tile
-  // element-wise operator (filled when requested)
-  std::vector<unsigned short> pair_loc;    // ebe_index(pair, b): position of cell node b in the tile's unique list
-  std::vector<unsigned short> pair_ca;     // [pairs] (position of the cell in the tile's cell list) << 4 | local node
-  std::vector<int> tile_cell_ptr, tile_cells;
-  int max_ucells = 0;
   int n_tiles() const { return (int)node_ptr.size() - 1; }
 };
-// index of (pair p, cell node b) in the blocked pair arrays (two consecutive b per lane element, 32 pairs per row)
-inline size_t ebe_pair_index(int NN, int64_t p, int b) {
-  return ((size_t)(p >> 5) * (size_t)(NN / 2) + (size_t)(b >> 1)) * 64 + (size_t)(p & 31) * 2 + (size_t)(b & 1);
-}
 // Returns an empty string on success, else an error message.
-std::string build_tile_plan(const Structure& S, const TileLimits& L, bool with_elementwise, TilePlan& P);
+std::string build_tile_plan(const Structure& S, const TileLimits& L, TilePlan& P);
 // Independent check of every invariant the kernels rely on; returns the number of violations (0 = consistent).
 int64_t verify_tile_plan(const Structure& S, const TileLimits& L, const TilePlan& P);
+
+// Streamed velocity operator (velstream.cuh).  The dim x dim blocks (node, neighbour node) of every owned node are grouped
+// in QUADS of four consecutive blocks (a node's list is padded to a multiple of four with zero blocks), one lane of a warp
+// handles one quad.  Per tile: a 64-byte header; per quad four metadata words (positions of the four neighbours in the
+// tile's unique list as 16-bit pairs, index of the quad's node in the tile or 0xffff for padding, first block index within
+// the node | real blocks << 16); tiles are padded to NQ = quads rounded up to 32, so every tile's value chunk (dim*dim
+// planes of NQ x 4 values) and metadata chunk move with one TMA bulk copy each.  split[] = node-aligned quad offsets that
+// divide the tile among the consumer warps.
+constexpr int VS_CONSUMERS = 8;                    // consumer warps that share one tile
+constexpr int VS_MAX_BLOCKS = 2048;                 // blocks per tile including the padding to quads
+constexpr int VS_MAX_QUADS = VS_MAX_BLOCKS / 4;
+struct alignas(16) VsTile {
+  int n0, nn;                              // first owned node, node count
+  int nquad, NQ;                           // quads, quads rounded up to a multiple of 32
+  int nq_off;                              // sum of NQ over the preceding tiles (metadata: 4 words per quad; values: dim*dim*4 per quad)
+  int u0, nuq;                             // the tile's unique neighbour list in TilePlan::uniq_xoff
+  int pad0;
+  unsigned short split[VS_CONSUMERS + 1];
+  unsigned short pad1[32 - 16 - (VS_CONSUMERS + 1)];
+};
+static_assert(sizeof(VsTile) == 64, "VsTile is one 64-byte TMA bulk copy");
+struct VsPlan {
+  std::vector<VsTile> tiles;
+  std::vector<uint32_t> meta;              // [4 * sum NQ]
+  int64_t total_nq = 0;
+};
+std::string build_vel_stream(const Structure& S, const TilePlan& P, VsPlan& V);
+// independent check (CPU tests): every block of every owned node appears once, in order, with the right neighbour;
+// splits are node-aligned and monotone; returns the number of violations
+int64_t verify_vel_stream(const Structure& S, const TilePlan& P, const VsPlan& V);
 
 // Expands the local rows to scalar CSR with GLOBAL column indices, rows in local owned
 // order (velocity rows then pressure rows); for the bit-exact pattern check.

@@ -562,7 +562,7 @@ static void kp_solve(const csr_t *Kp, const ilu_t *Fk, const double *t, double *
   memset(x, 0, sizeof(double) * n);
   memcpy(r, t, sizeof(double) * n);
   const double r0 = sqrt(dotp(n, r, r));
-  if (r0 == 0) return;
+  if (r0 == 0 || r0 != r0) return;
   ilu_apply(Fk, r, z);
   memcpy(p, z, sizeof(double) * n);
   double rz = dotp(n, r, z);
@@ -570,7 +570,8 @@ static void kp_solve(const csr_t *Kp, const ilu_t *Fk, const double *t, double *
     csr_mv(Kp, p, q);
     const double alpha = rz / dotp(n, p, q);
     for (int i = 0; i < n; ++i) { x[i] += alpha * p[i]; r[i] -= alpha * q[i]; }
-    if (sqrt(dotp(n, r, r)) <= rtol * r0) break;
+    const double rn_ = sqrt(dotp(n, r, r));
+    if (rn_ <= rtol * r0 || rn_ != rn_) break;
     ilu_apply(Fk, r, z);
     const double rz2 = dotp(n, r, z);
     const double beta = rz2 / rz;
@@ -583,6 +584,7 @@ static void kp_solve(const csr_t *Kp, const ilu_t *Fk, const double *t, double *
 /* Core: A as full scalar CSR (used in place, not copied), the (1,1) blocks of M_p / K_p as a compact CSR over the pressure
  * DoFs (shared pattern pp_ptr / pp_col).  time_budget_s > 0: stop iterating once the solve has run that long (the result is
  * then reported as not converged; bench.py's reference arm uses it to stay inside its time limit).
+ * Returns 0 converged, 1 max_it reached, 2 stopped by the time budget, 3 the residual became NaN (ILU breakdown).
  * timings[4] (optional) = {preconditioner setup, GMRES iterations, K_p CG inside them, total} in seconds. */
 int nso_solve_blocks(int64_t N, int64_t n_u, const int64_t *rowptr, const int32_t *col, const double *A, const int64_t *pp_ptr,
                      const int32_t *pp_col, const double *Mp, const double *Kp, const double *b, double nu, double rho,
@@ -681,6 +683,7 @@ int nso_solve_blocks(int64_t N, int64_t n_u, const int64_t *rowptr, const int32_
       if (getenv("NSO_DEBUG") && it % 10 == 0) fprintf(stderr, "[nso] it %d res %.4e (tol %.4e)\n", it, res, tol);
       if (res <= tol) { conv = 1; break; }
       if (it >= max_it) break;
+      if (res != res) { out_of_time = 2; break; }         /* NaN: SolverControl::check reports failure at once (deal.II) */
       if (time_budget_s > 0 && omp_get_wtime() - t_setup0 > time_budget_s) { out_of_time = 1; break; }
     }
     for (int i = kused - 1; i >= 0; --i) {
@@ -703,7 +706,7 @@ int nso_solve_blocks(int64_t N, int64_t n_u, const int64_t *rowptr, const int32_
   free(V); free(w); free(tmp); free(tp); free(t2); free(y1); free(wk); free(H); free(cs); free(sn); free(g); free(yv);
   ilu_free(&iF); ilu_free(&iM); ilu_free(&iK);
   csr_free(&B);
-  return out_of_time ? 2 : rc;
+  return out_of_time == 2 ? 3 : out_of_time ? 2 : rc;
 }
 
 /* M_p / K_p given on the FULL pattern (as assemble_impl writes them): extract the (1,1) blocks and solve. */

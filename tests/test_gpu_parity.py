@@ -276,7 +276,7 @@ def test_full_size_properties_mesh_3d_10(nsb):
 
 
 def test_solver_options_reach_the_same_solution(case3d):
-    """fp64 vs fp32 operator inside the velocity polynomial, Chebyshev vs harmonic-Ritz roots, the reference's
+    """fp64 / fp32 / fp16 operator copies inside the velocity polynomial, Chebyshev vs harmonic-Ritz roots, the reference's
     theta*nu Schur scaling: different preconditioners, same linear system => same tight-tolerance solution."""
     c = case3d
     nsb = c.nsb
@@ -287,7 +287,7 @@ def test_solver_options_reach_the_same_solution(case3d):
     x0 = c.dev.get_vector(nsb.NSB_SOLUTION)
     assert ok
     for opts in (dict(precond_precision=64), dict(poly_kind=-1), dict(poly_target=0.2, poly_degree_F=8),
-                 dict(schur_mass_coeff=0.5 * c.nu), dict(precond_operator=1), dict(precond_operator=2)):
+                 dict(schur_mass_coeff=0.5 * c.nu), dict(precond_precision=32), dict(precond_precision=16)):
         c.dev.set_solver_opts(**opts)
         c.dev.assemble_linearized()            # refills the operator copy after a precision change
         ok, it, _ = c.dev.solve(3000, 1e-12, 150)
@@ -339,11 +339,11 @@ def test_newton_iterations_3d_supg_match_oracle(case3d):
 
 
 @pytest.mark.parametrize("which", ["2d", "3d"])
-def test_elementwise_velocity_operator_equals_assembled(case2d, case3d, which):
-    """The element-wise application of the velocity block (precond_operator=2: per-pair rows of S_e in fp32 + the
-    grad-div part rebuilt from the cell geometry) is the same operator as the assembled one (precond_operator=1),
-    including Dirichlet rows / columns: checked against the fp64 assembled values on random vectors, in every u*
-    regime, and through identical GMRES iteration counts at the reference's stopping rule."""
+def test_streamed_velocity_operator_equals_assembled(case2d, case3d, which):
+    """The streamed velocity operator (velstream.cuh: packed fp32 / fp16 copy of Dinv F, TMA-staged tiles, segmented warp
+    scans) is the same operator as the generic fp64 row kernel on the assembled values (precond_precision=64), including
+    Dinv-scaled Dirichlet rows: checked on random vectors in two u* regimes, bit-reproducible from call to call, and
+    through the GMRES iteration counts at the reference's stopping rule."""
     c = case2d if which == "2d" else case3d
     nsb = c.nsb
     con = c.constraints()
@@ -353,23 +353,24 @@ def test_elementwise_velocity_operator_equals_assembled(case2d, case3d, which):
     try:
         for theta, first in ((0.5, False), (1.0, True)):
             ys, its = {}, {}
-            for op, prec in ((1, 64), (1, 32), (2, 32)):
-                c.dev.set_solver_opts(precond_operator=op, precond_precision=prec)
+            for prec in (64, 32, 16):
+                c.dev.set_solver_opts(precond_precision=prec)
                 c.linearized(theta, first, con)
                 c.dev.assemble_pressure_matrices()
-                ys[(op, prec)] = c.dev.apply_velocity_block(x)[:n_u]
+                ys[prec] = c.dev.apply_velocity_block(x)[:n_u]
+                assert np.array_equal(ys[prec], c.dev.apply_velocity_block(x)[:n_u])
                 ok, it, _ = c.dev.solve(200, 1e-2, 150)
                 assert ok
-                its[(op, prec)] = it
-            ref = ys[(1, 64)]
+                its[prec] = it
+            ref = ys[64]
             assert np.abs(ref).max() > 0
-            e32 = np.linalg.norm(ys[(1, 32)] - ref) / np.linalg.norm(ref)
-            ebe = np.linalg.norm(ys[(2, 32)] - ref) / np.linalg.norm(ref)
-            assert e32 < 1e-5 and ebe < 1e-5, (e32, ebe)
+            e32 = np.linalg.norm(ys[32] - ref) / np.linalg.norm(ref)
+            e16 = np.linalg.norm(ys[16] - ref) / np.linalg.norm(ref)
+            assert e32 < 1e-6 and e16 < 5e-3, (e32, e16)
             # Dirichlet rows act as the identity after the block-Jacobi scaling
             cu = con.dofs[con.dofs < n_u]
-            assert np.allclose(ys[(2, 32)][cu], x[cu], rtol=1e-12, atol=0)
-            assert abs(its[(2, 32)] - its[(1, 32)]) <= 1, its
+            assert np.allclose(ys[32][cu], x[cu], rtol=1e-12, atol=0) and np.allclose(ys[16][cu], x[cu], rtol=1e-12, atol=0)
+            assert abs(its[32] - its[64]) <= 1 and abs(its[16] - its[64]) <= 2, its
     finally:
         c.dev.set_solver_opts()
         c.linearized(0.5, False, con)

@@ -172,9 +172,10 @@ def test_hessenberg_eigenvalues():
 
 @pytest.mark.parametrize("which", ["2d", "3d"])
 def test_spmv_tile_plan_invariants(golden_mesh, small_3d_mesh, which):
-    """The host-built plan the SpMV / element-wise kernels consume (tile ranges, unique neighbour lists, 16-bit
-    positions, interior / boundary split, per-pair arrays) passes the independent C++ verifier on one rank and on
-    every rank of 2- and 3-way partitions; a single rank has no boundary tile, partitioned ranks have some."""
+    """The host-built plans the SpMV kernels and the streamed velocity operator consume (tile ranges, unique neighbour
+    lists, 16-bit positions, interior / boundary split; per tile the padded block count, the block metadata words and the
+    node-aligned split among the consumer warps) pass the independent C++ verifiers on one rank and on every rank of 2-
+    and 3-way partitions; a single rank has no boundary tile, partitioned ranks have some."""
     lib = C.CDLL(LIB, mode=C.RTLD_GLOBAL)
     m = golden_mesh("mesh-2D") if which == "2d" else small_3d_mesh
     dm = odofs.enumerate_dofs(m)
@@ -185,13 +186,13 @@ def test_spmv_tile_plan_invariants(golden_mesh, small_3d_mesh, which):
     for nranks in (1, 2, 3):
         part = (np.arange(m.n_cells, dtype=np.int64) * nranks // m.n_cells).astype(np.int32)
         for rank in range(nranks):
-            for ebe in (0, 1):
-                out = np.zeros(5, np.int64)
-                rc = lib.nsb_test_tile_plan(m.dim, C.c_int64(pts.shape[0]), P(pts, C.c_double), C.c_int64(cv.shape[0]), P(cv, C.c_uint32),
-                                            P(cd, C.c_uint32), C.c_int64(dm.n_u), C.c_int64(dm.n_p),
-                                            P(part, C.c_int32) if nranks > 1 else None, rank, nranks, ebe, P(out, C.c_int64))
-                assert rc == 0
-                tiles, n_int, n_bnd, max_pairs, bad = out
-                assert bad == 0, (nranks, rank, ebe, out)
-                assert tiles > 0 and n_int + n_bnd == tiles and max_pairs > 0
-                assert (n_bnd == 0) if nranks == 1 else (n_bnd > 0)
+            out = np.zeros(5, np.int64)
+            rc = lib.nsb_test_tile_plan(m.dim, C.c_int64(pts.shape[0]), P(pts, C.c_double), C.c_int64(cv.shape[0]), P(cv, C.c_uint32),
+                                        P(cd, C.c_uint32), C.c_int64(dm.n_u), C.c_int64(dm.n_p),
+                                        P(part, C.c_int32) if nranks > 1 else None, rank, nranks, P(out, C.c_int64))
+            assert rc == 0
+            tiles, n_int, n_bnd, padded_blocks, bad = out
+            assert bad == 0, (nranks, rank, out)
+            assert tiles > 0 and n_int + n_bnd == tiles
+            assert (n_bnd == 0) if nranks == 1 else (n_bnd > 0)
+            assert padded_blocks % 32 == 0 and padded_blocks > 0      # streamed operator: blocks rounded up to 32 per tile
