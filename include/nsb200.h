@@ -56,6 +56,12 @@ typedef struct nsb_solver_opts {
                                assembled fp64 values themselves.  Changing it invalidates the assembled system
                                (re-assemble before solving). */
   int32_t precond_operator; /* reserved (round 1's element-wise operator was removed); ignored */
+  int32_t velocity_cycle;   /* 2 (default, also 0) = two-level cycle on the velocity block of LINEARISED systems whose scaled
+                               spectrum is real: P1 coarse space (Galerkin operator, Chebyshev solve) + Chebyshev smoother;
+                               1 = the single-level polynomial only.  Newton systems and complex spectra always use 1. */
+  int32_t smoother_degree;  /* operator applications of the fine-level smoother per cycle      (default 6)    */
+  double smoother_lo_frac;  /* smoother interval [frac * lambda_max, lambda_max]               (default 0.05) */
+  int32_t coarse_degree;    /* Chebyshev degree of the coarse solve                            (default 15)   */
 } nsb_solver_opts;
 
 /* ---- lifetime -------------------------------------------------------------------- */
@@ -149,7 +155,7 @@ int nsb_timer_start(nsb_handle h);
 int nsb_timer_stop(nsb_handle h, double* milliseconds);
 int nsb_synchronize(nsb_handle h);
 /* per-kernel-class CUDA-event profile: names "asm_context","asm_rows","spmv","spmv_vel",
- * "schur","amg","orth","other","asm_pack" */
+ * "schur","amg","orth","other","asm_pack","coarse","asm_coarse" */
 int nsb_profile_enable(nsb_handle h, int on);
 int nsb_profile_reset(nsb_handle h);
 int nsb_profile_get(nsb_handle h, const char* name, double* total_ms, int64_t* launches);
@@ -160,6 +166,15 @@ int nsb_solver_info(nsb_handle h, int* poly_degree, double* poly_probe_residual,
  * array, bytes of its index side (block metadata, tile headers, unique-neighbour lists), tiles, (node, neighbour) blocks */
 int nsb_velocity_operator_info(nsb_handle h, int* precision, int64_t* value_bytes, int64_t* index_bytes, int64_t* tiles,
                                int64_t* blocks);
+/* inspection (parity tests): the Galerkin coarse operator P^T F P of the two-level velocity cycle as block CSR over the owned
+ * vertices -- global vertex id of every row, block row pointer, global vertex id of every block column, dim*dim values per
+ * block (row-major).  NULL arrays are skipped (call once for the sizes). */
+int nsb_get_coarse_operator(nsb_handle h, int64_t* n_rows, int64_t* n_blocks, int64_t* row_gid, int64_t* rowptr, int64_t* col_gid,
+                            double* vals);
+/* the velocity preconditioner as set up by the last solve: two-level cycle or not, smoother / coarse degrees, coarse rows,
+ * bytes of the packed coarse operator, estimate of lambda_max(Dinv F) */
+int nsb_velocity_pc_info(nsb_handle h, int* two_level, int* smoother_degree, int* coarse_degree, int64_t* coarse_rows,
+                         int64_t* coarse_value_bytes, double* fine_lambda_max);
 /* how many kernels this library launched since nsb_create */
 int nsb_launch_count(nsb_handle h, int64_t* n);
 

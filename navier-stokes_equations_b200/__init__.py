@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NSB200_LIB", os.path.join(_HERE, "libnsb200.so"))   # override: kernel-variant experiments
 
 NSB_SOLUTION_OLD, NSB_SOLUTION_OLD_OLD, NSB_CURRENT_SOLUTION, NSB_SOLUTION, NSB_RHS = 0, 1, 2, 3, 4
-PROFILE_CLASSES = ("asm_context", "asm_rows", "spmv", "spmv_vel", "schur", "amg", "orth", "other", "asm_pack")
+PROFILE_CLASSES = ("asm_context", "asm_rows", "spmv", "spmv_vel", "schur", "amg", "orth", "other", "asm_pack", "coarse", "asm_coarse")
 
 
 class NsbError(RuntimeError):
@@ -32,7 +32,8 @@ class NsbParams(C.Structure):
 class NsbSolverOpts(C.Structure):
     _fields_ = [("poly_degree_F", C.c_int32), ("poly_refresh", C.c_int32), ("poly_kind", C.c_int32), ("poly_target", C.c_double), ("cheb_degree_Mp", C.c_int32),
                 ("amg_smoother_degree", C.c_int32), ("schur_mass_coeff", C.c_double), ("reorthogonalize", C.c_int32), ("precond_precision", C.c_int32),
-                ("precond_operator", C.c_int32)]
+                ("precond_operator", C.c_int32), ("velocity_cycle", C.c_int32), ("smoother_degree", C.c_int32),
+                ("smoother_lo_frac", C.c_double), ("coarse_degree", C.c_int32)]
 
 
 _lib = None
@@ -142,9 +143,10 @@ class Device:
         self._ck(lib().nsb_set_params(self.h, C.byref(p)))
 
     def set_solver_opts(self, poly_degree_F=0, poly_refresh=0, poly_kind=0, poly_target=0.0, cheb_degree_Mp=0, amg_smoother_degree=0,
-                        schur_mass_coeff=0.0, reorthogonalize=0, precond_precision=0, precond_operator=0):
+                        schur_mass_coeff=0.0, reorthogonalize=0, precond_precision=0, precond_operator=0, velocity_cycle=0,
+                        smoother_degree=0, smoother_lo_frac=0.0, coarse_degree=0):
         o = NsbSolverOpts(poly_degree_F, poly_refresh, poly_kind, poly_target, cheb_degree_Mp, amg_smoother_degree, schur_mass_coeff, reorthogonalize, precond_precision,
-                          precond_operator)
+                          precond_operator, velocity_cycle, smoother_degree, smoother_lo_frac, coarse_degree)
         self._ck(lib().nsb_set_solver_opts(self.h, C.byref(o)))
 
     def get_solver_opts(self):
@@ -253,6 +255,23 @@ class Device:
         v = [C.c_int64() for _ in range(4)]
         self._ck(lib().nsb_velocity_operator_info(self.h, C.byref(p), *[C.byref(x) for x in v]))
         return dict(precision=p.value, value_bytes=v[0].value, index_bytes=v[1].value, tiles=v[2].value, blocks=v[3].value)
+
+    def coarse_operator(self):
+        """(row_gid, rowptr, col_gid, vals[nblocks, dim, dim]) of the Galerkin coarse operator (owned vertices)."""
+        n, nb = C.c_int64(), C.c_int64()
+        self._ck(lib().nsb_get_coarse_operator(self.h, C.byref(n), C.byref(nb), None, None, None, None))
+        rg, rp, cg = np.empty(n.value, np.int64), np.empty(n.value + 1, np.int64), np.empty(nb.value, np.int64)
+        v = np.empty((nb.value, self.dim, self.dim))
+        self._ck(lib().nsb_get_coarse_operator(self.h, C.byref(n), C.byref(nb), _p(rg, C.c_int64), _p(rp, C.c_int64), _p(cg, C.c_int64), _p(v, C.c_double)))
+        return rg, rp, cg, v
+
+    def velocity_pc_info(self):
+        a, b, d = C.c_int(), C.c_int(), C.c_int()
+        r, v = C.c_int64(), C.c_int64()
+        lm = C.c_double()
+        self._ck(lib().nsb_velocity_pc_info(self.h, C.byref(a), C.byref(b), C.byref(d), C.byref(r), C.byref(v), C.byref(lm)))
+        return dict(two_level=bool(a.value), smoother_degree=b.value, coarse_degree=d.value, coarse_rows=r.value,
+                    coarse_value_bytes=v.value, fine_lambda_max=lm.value)
 
     def launch_count(self):
         n = C.c_int64()

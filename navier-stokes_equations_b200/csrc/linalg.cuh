@@ -237,6 +237,7 @@ k_spmv_full(DevMesh M, SpmvTiles TL, const VT* __restrict__ vals, const double* 
 // (reference NavierStokes.hpp:302-304, 325).  Dinv = inverse node-diagonal blocks.
 //   MODE 0:  y = F x
 //   MODE 2:  y = Dinv (F x)                                     (Arnoldi on the scaled block)
+//   MODE 4:  t = Dinv (F x) ; y = cu*u + ct*t
 //   MODE 3:  t = Dinv (F x) ; y = cu*u + ct*t ; poly += cpu*u + cpy*y   (one root of the
 //            GMRES polynomial in product form; u is read at the node's own entries)
 // ------------------------------------------------------------------------------------
@@ -259,7 +260,7 @@ __device__ __forceinline__ void vel_prefetch(int A, int lane, const double* __re
   if (MODE != 0 && lane < DIM) {
 #pragma unroll
     for (int c = 0; c < DIM; ++c) e.dv[c] = __ldg(dinv + (size_t)A * DIM * DIM + lane * DIM + c);
-    if (MODE == 3) { e.uv = u[DIM * A + lane]; e.pv = poly[DIM * A + lane]; }
+    if (MODE >= 3) { e.uv = u[DIM * A + lane]; if (MODE == 3) e.pv = poly[DIM * A + lane]; }
   }
 }
 
@@ -282,7 +283,7 @@ __device__ __forceinline__ void vel_epilogue(int A, int lane, const double (&sum
       } else {
         const double yv = pc.cu * e.uv + pc.ct * t;
         y[row] = yv;
-        poly[row] = e.pv + pc.cpu * e.uv + pc.cpy * yv;
+        if (MODE == 3) poly[row] = e.pv + pc.cpu * e.uv + pc.cpy * yv;
       }
     }
   }

@@ -22,6 +22,7 @@
 #include "device.cuh"
 #include "linalg.cuh"
 #include "structure.hpp"
+#include "twolevel.cuh"
 #include "velstream.cuh"
 
 using namespace nsb;
@@ -100,8 +101,8 @@ template <typename T> struct DBuf {
   }
 };
 
-enum ProfCat { PC_ASM_CTX = 0, PC_ASM_ROWS, PC_SPMV, PC_SPMV_VEL, PC_SCHUR, PC_AMG, PC_ORTH, PC_OTHER, PC_ASM_PACK, PC_N };
-const char* kProfNames[PC_N] = {"asm_context", "asm_rows", "spmv", "spmv_vel", "schur", "amg", "orth", "other", "asm_pack"};
+enum ProfCat { PC_ASM_CTX = 0, PC_ASM_ROWS, PC_SPMV, PC_SPMV_VEL, PC_SCHUR, PC_AMG, PC_ORTH, PC_OTHER, PC_ASM_PACK, PC_COARSE, PC_ASM_COARSE, PC_N };
+const char* kProfNames[PC_N] = {"asm_context", "asm_rows", "spmv", "spmv_vel", "schur", "amg", "orth", "other", "asm_pack", "coarse", "asm_coarse"};
 
 struct Prof {
   bool on = false;
@@ -161,6 +162,45 @@ void upload_csr(const HostCsr& H, DBuf<int>& ptr, DBuf<int>& col, DBuf<double>& 
   ptr.upload(H.ptr, s); col.upload(H.col, s); val.upload(H.val, s);
   D.n = H.n; D.m = H.m; D.ptr = ptr.p; D.col = col.p; D.val = val.p;
 }
+
+// device view of one streamed operator (velstream.cuh)
+struct VsDev {
+  const VsTile* tiles;
+  const uint32_t* meta;
+  const int* uniq_xoff;
+  const unsigned char* vals;
+  int n_tiles;
+};
+
+// one level of the velocity preconditioner: sizes, work vectors, spectrum estimate and polynomial roots
+struct PolyLevel {
+  bool coarse = false;
+  int nn = 0;                          // owned nodes
+  long long n = 0, n_tot = 0;          // owned entries (dim * nn), entries including ghosts
+  const double* dinv = nullptr;        // inverse node-diagonal blocks
+  const int64_t* gid = nullptr;        // global node ids (probe vector)
+  double *z0 = nullptr, *z1 = nullptr, *zd = nullptr, *poly = nullptr, *pin = nullptr;
+  DBuf<double> probe;
+  bool probe_init = false;
+  std::vector<double> wr, wi;          // harmonic Ritz values of the last Arnoldi run
+  double ritz_lo = 0, ritz_hi = 0, ritz_im = 0, probe_res = 1.0;
+  std::vector<std::pair<double, double>> roots;   // (re, im >= 0), Leja ordered
+};
+
+// coarse P1 level of the two-level cycle (twolevel.cuh)
+struct Coarse {
+  DBuf<VsTile> tiles;
+  DBuf<uint32_t> meta;
+  DBuf<int> uniq_xoff;
+  DBuf<unsigned char> vals;            // packed Dinv_c F_c
+  int n_tiles = 0;
+  int64_t total_nq = 0;
+  DBuf<long long> nbr_ptr, vedge_ptr;
+  DBuf<int> nbr_vxoff, vedge_xoff, ends_xoff, send_xoff;
+  DBuf<double> cvals, dinv, rc, z0, z1, zd, poly, pin, send_buf;
+  std::vector<int64_t> gid, h_nbr_ptr, h_nbr_gid;     // host copies: global vertex ids of the owned rows / of the neighbours
+  bool built = false, valid = false;   // structures uploaded / operator matches the assembled system
+};
 
 }  // namespace
 
@@ -238,14 +278,13 @@ struct nsb_ctx {
   DBuf<double> coarse_inv;
   int coarse_n = 0;
   // preconditioner / Krylov workspace
-  DBuf<double> w_z0, w_z1, w_d, w_t, w_y1, w_m0, w_m1, w_md, w_in, w_tmp, w_pin, w_poly;
-  double poly_probe_res = 1.0;
-  std::vector<std::pair<double, double>> poly_roots;   // harmonic Ritz values (re, im>=0), Leja ordered
+  DBuf<double> w_z0, w_z1, w_d, w_t, w_y1, w_m0, w_m1, w_md, w_in, w_tmp, w_pin, w_poly, w_y0, w_u;
+  Coarse cg;
+  PolyLevel lvF, lvC;
+  bool two_level = false;           // the last setup chose the two-level cycle
   DBuf<double> V;                   // Krylov basis, (m+1) vectors of n_own
   int V_cap = 0;
   DBuf<double> partial, d_h, d_nrm;
-  DBuf<double> eigv;                // power-iteration vector for lambda_max(Dinv F)
-  bool eig_init = false;
   int solves = 0;
 
   void launch_check() {
@@ -353,6 +392,8 @@ void allreduce_sum(nsb_ctx* c, double* dbuf, int n) {
 }
 
 // ---- templated launch helpers --------------------------------------------------------
+template <int DIM> void launch_coarse_assemble(nsb_ctx* c);
+
 template <int DIM> void launch_assemble(nsb_ctx* c, bool newton) {
   AsmParams P;
   P.dt = c->par.dt; P.inv_dt = 1.0 / c->par.dt; P.theta = c->par.theta; P.nu = c->par.nu; P.rho = c->par.rho;
@@ -394,6 +435,9 @@ template <int DIM> void launch_assemble(nsb_ctx* c, bool newton) {
     c->prof.end(id, c->stream);
     c->vs_valid = true;
   }
+  // Galerkin coarse operator of the two-level cycle (linearised systems: their cell context holds S_ab)
+  c->cg.valid = false;
+  if (!newton && c->vs_valid && c->cg.built && c->opt.velocity_cycle != 1) launch_coarse_assemble<DIM>(c);
 }
 
 template <int DIM> void set_smem_attr(int bytes) {
@@ -406,28 +450,30 @@ template <int DIM, typename VT> void set_vs_attr() {
   CK(cudaFuncSetAttribute(k_vel_stream<DIM, VT, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute(k_vel_stream<DIM, VT, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute(k_vel_stream<DIM, VT, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CK(cudaFuncSetAttribute(k_vel_stream<DIM, VT, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 }
 
 // one application of the streamed operator over `ntiles` tiles (all of them, or the listed ones)
 template <int DIM, typename VT, int MODE, bool LISTED>
-void launch_vel_stream(nsb_ctx* c, int ntiles, const int* list, const double* x, double* y, const double* u, double* poly, PolyCoef pc) {
+void launch_vel_stream(nsb_ctx* c, const VsDev& D, int ntiles, const int* list, const double* x, double* y, const double* u, double* poly, PolyCoef pc) {
   if (ntiles <= 0) return;
   const int grid = std::min(ntiles, c->num_sms);
   k_vel_stream<DIM, VT, MODE, LISTED><<<grid, VS_THREADS, VsLayout<DIM, VT>::SMEM_BYTES, c->stream>>>(
-      c->d_vs_tiles.p, ntiles, list, reinterpret_cast<const VT*>(c->vs_vals.p), c->d_vs_meta.p, c->d_suniq_xoff.p, x, y, u, poly, pc);
+      D.tiles, ntiles, list, reinterpret_cast<const VT*>(D.vals), D.meta, D.uniq_xoff, x, y, u, poly, pc);
   c->launch_check();
 }
 template <int MODE, bool LISTED>
-void vel_stream(nsb_ctx* c, int ntiles, const int* list, const double* x, double* y, const double* u, double* poly, PolyCoef pc) {
+void vel_stream(nsb_ctx* c, const VsDev& D, int ntiles, const int* list, const double* x, double* y, const double* u, double* poly, PolyCoef pc) {
   const bool h = c->opt.precond_precision == 16;
   if (c->dim == 2) {
-    if (h) launch_vel_stream<2, __half, MODE, LISTED>(c, ntiles, list, x, y, u, poly, pc);
-    else launch_vel_stream<2, float, MODE, LISTED>(c, ntiles, list, x, y, u, poly, pc);
+    if (h) launch_vel_stream<2, __half, MODE, LISTED>(c, D, ntiles, list, x, y, u, poly, pc);
+    else launch_vel_stream<2, float, MODE, LISTED>(c, D, ntiles, list, x, y, u, poly, pc);
   } else {
-    if (h) launch_vel_stream<3, __half, MODE, LISTED>(c, ntiles, list, x, y, u, poly, pc);
-    else launch_vel_stream<3, float, MODE, LISTED>(c, ntiles, list, x, y, u, poly, pc);
+    if (h) launch_vel_stream<3, __half, MODE, LISTED>(c, D, ntiles, list, x, y, u, poly, pc);
+    else launch_vel_stream<3, float, MODE, LISTED>(c, D, ntiles, list, x, y, u, poly, pc);
   }
 }
+VsDev fine_dev(const nsb_ctx* c);
 
 // y(owned) = A x ; x must have a valid ghost tail
 void spmv_full(nsb_ctx* c, const double* x, double* y) {
@@ -443,7 +489,7 @@ void spmv_vel(nsb_ctx* c, const double* x, double* y, const double* u, double* p
   size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
   const int g = c->n_stiles;
   if (c->vs_valid && MODE != 0) {
-    vel_stream<MODE == 0 ? 2 : MODE, false>(c, g, nullptr, x, y, u, poly, pc);
+    vel_stream<MODE == 0 ? 2 : MODE, false>(c, fine_dev(c), g, nullptr, x, y, u, poly, pc);
   } else {
     if (c->dim == 2) k_spmv_vel<2, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, c->vals.p, x, y, u, poly, c->dinv.p, pc);
     else k_spmv_vel<3, MODE, double><<<g, SPMV_WARPS * 32, 0, c->stream>>>(c->M, c->stiles, c->vals.p, x, y, u, poly, c->dinv.p, pc);
@@ -463,9 +509,9 @@ void halo_spmv_vel3(nsb_ctx* c, double* x, double* y, const double* u, double* p
   }
   halo_start_velocity(c, x);
   size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
-  vel_stream<3, true>(c, c->n_tiles_int, c->d_tiles_int.p, x, y, u, poly, pc);
+  vel_stream<3, true>(c, fine_dev(c), c->n_tiles_int, c->d_tiles_int.p, x, y, u, poly, pc);
   CK(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
-  vel_stream<3, true>(c, c->n_tiles_bnd, c->d_tiles_bnd.p, x, y, u, poly, pc);
+  vel_stream<3, true>(c, fine_dev(c), c->n_tiles_bnd, c->d_tiles_bnd.p, x, y, u, poly, pc);
   c->prof.end(id, c->stream);
 }
 
@@ -504,81 +550,136 @@ struct Cheb {
   }
 };
 
-// ---- GMRES polynomial for the velocity block ---------------------------------------------
-// p(B) ~ B^-1 with B = Dinv F (node-block-Jacobi scaled), p of degree d-1 defined by the
-// harmonic Ritz values theta_i of d Arnoldi steps from a fixed pseudo-random vector
-// (Loe & Morgan's polynomial preconditioned GMRES).  p is a FIXED linear operator between
-// rebuilds, so the outer iteration stays plain (non-flexible) left-preconditioned GMRES like
-// the reference's.  Robust for the convection-dominated (complex) spectrum where Chebyshev
-// on a real interval diverges.
+// ---- velocity-block preconditioner ---------------------------------------------------------
+// Everything here works on B = Dinv F, the node-block-Jacobi scaled velocity block, on one of two levels: the fine (P2)
+// level and, for linearised systems, the coarse P1 level of the two-level cycle (twolevel.cuh).  A level's operator is applied
+// by the streamed kernel (velstream.cuh) -- the fine level falls back to the generic fp64 row kernel when no packed copy
+// is kept.  Polynomials are FIXED linear operators between rebuilds, so the outer iteration stays plain (non-flexible)
+// left-preconditioned GMRES like the reference's.
 
-void setup_F_poly(nsb_ctx* c) {
+VsDev fine_dev(const nsb_ctx* c) {
+  return VsDev{c->d_vs_tiles.p, c->d_vs_meta.p, c->d_suniq_xoff.p, c->vs_vals.p, c->n_stiles};
+}
+VsDev coarse_dev(const nsb_ctx* c) {
+  return VsDev{c->cg.tiles.p, c->cg.meta.p, c->cg.uniq_xoff.p, c->cg.vals.p, c->cg.n_tiles};
+}
+
+// halo of a coarse vector (layout [dim*np_own | dim*np_ghost]): the pressure halo plan with dim components per vertex
+void halo_exchange_coarse(nsb_ctx* c, double* v) {
+  if (c->nranks == 1) return;
   const Structure& S = c->S;
-  const long long nu = (long long)c->dim * S.nn_own;
-  const long long n = S.n_own_dofs();
-  int d = std::max(1, std::min(c->opt.poly_degree_F, 64));
-  if (c->V_cap < d + 1) { c->V.alloc((size_t)(std::max(d + 1, c->V_cap)) * n); c->V_cap = std::max(d + 1, c->V_cap); }
-  const int nb = nblk(nu, RED_CHUNK);
+  Coarse& G = c->cg;
+  const int dim = c->dim;
+  const long long tp = (long long)G.send_xoff.n;
+  if (tp) { k_gather_nodes<<<nblk(tp * dim, 256), 256, 0, c->stream>>>((int)tp, dim, G.send_xoff.p, v, G.send_buf.p); c->launch_check(); }
+  CKN(g_nccl.GroupStart());
+  long long roff = (long long)dim * S.np_own;
+  size_t so = 0;
+  for (size_t k = 0; k < S.peer.size(); ++k) {
+    const int peer = S.peer[k];
+    const size_t ns = S.send_pids[k].size() * dim, nr = (size_t)S.recv_pid_count[k] * dim;
+    if (ns) CKN(g_nccl.Send(G.send_buf.p + so, ns, ncclDouble, peer, c->comm, c->stream));
+    if (nr) CKN(g_nccl.Recv(v + roff, nr, ncclDouble, peer, c->comm, c->stream));
+    so += ns; roff += nr;
+  }
+  CKN(g_nccl.GroupEnd());
+}
+
+void level_halo(nsb_ctx* c, PolyLevel& lv, double* v) {
+  if (lv.coarse) halo_exchange_coarse(c, v);
+  else halo_exchange(c, v, false);
+}
+
+// y = op(B x) with the fused epilogue MODE (2, 3 or 4); x must have valid ghosts
+template <int MODE>
+void level_apply(nsb_ctx* c, PolyLevel& lv, const double* x, double* y, const double* u, double* poly, PolyCoef pc) {
+  if (!lv.coarse) { spmv_vel<MODE>(c, x, y, u, poly, pc); return; }
+  size_t id = c->prof.begin(PC_COARSE, c->stream);
+  vel_stream<MODE, false>(c, coarse_dev(c), c->cg.n_tiles, nullptr, x, y, u, poly, pc);
+  c->prof.end(id, c->stream);
+}
+
+// one root of a product-form polynomial on a vector whose ghosts are stale
+void level_root(nsb_ctx* c, PolyLevel& lv, double* x, double* y, const double* u, double* poly, PolyCoef pc) {
+  if (!lv.coarse) { halo_spmv_vel3(c, x, y, u, poly, pc); return; }
+  halo_exchange_coarse(c, x);
+  level_apply<3>(c, lv, x, y, u, poly, pc);
+}
+
+void level_block_scale(nsb_ctx* c, PolyLevel& lv, const double* x, double* y) {
+  if (c->dim == 2) k_block_scale<2><<<nblk(lv.nn, 256), 256, 0, c->stream>>>(lv.nn, lv.dinv, x, y);
+  else k_block_scale<3><<<nblk(lv.nn, 256), 256, 0, c->stream>>>(lv.nn, lv.dinv, x, y);
+  c->launch_check();
+}
+
+// d Arnoldi steps on B from a fixed pseudo-random probe (a hash of the GLOBAL DoF index, so everything derived from it is
+// partition-independent); stops early once the GMRES residual of the probe drops below `target` (target <= 0: never).
+// Leaves the harmonic Ritz values in lv.wr / lv.wi and the probe's residual reduction in lv.probe_res.
+void level_arnoldi(nsb_ctx* c, PolyLevel& lv, int dmax, double target) {
+  const long long nl = lv.n;
+  const long long ld = c->S.n_own_dofs();          // stride of the Krylov basis (shared with GMRES, always >= nl)
+  int d = std::max(1, std::min(dmax, 64));
+  if (c->V_cap < d + 1) { c->V.alloc((size_t)(std::max(d + 1, c->V_cap)) * ld); c->V_cap = std::max(d + 1, c->V_cap); }
+  const int nb = nblk(nl, RED_CHUNK);
   if (c->partial.n < (size_t)nb * (d + 2)) c->partial.alloc((size_t)nb * (d + 2));
   if (c->d_h.n < (size_t)2 * (d + 2)) c->d_h.alloc(2 * (d + 2));
-  if (!c->eig_init) {
-    // pseudo-random probe, a function of the GLOBAL DoF index only -> the polynomial (and therefore the
-    // GMRES iteration count) does not depend on how the mesh is partitioned
-    std::vector<double> h(nu);
-    for (int A = 0; A < S.nn_own; ++A)
+  if (!lv.probe_init) {
+    std::vector<double> h(nl);
+    for (int A = 0; A < lv.nn; ++A)
       for (int k = 0; k < c->dim; ++k) {
-        uint64_t z = (uint64_t)(S.node_gid[A] * c->dim + k) + 0x9E3779B97F4A7C15ull;
+        uint64_t z = (uint64_t)(lv.gid[A] * c->dim + k) + 0x9E3779B97F4A7C15ull;
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
         z ^= z >> 31;
         h[(size_t)c->dim * A + k] = (double)(z >> 11) / 9007199254740992.0 - 0.5;
       }
-    c->eigv.upload(h, c->stream);
+    lv.probe.upload(h, c->stream);
     CK(cudaStreamSynchronize(c->stream));
-    c->eig_init = true;
+    lv.probe_init = true;
   }
+  const int ldh = d;
   std::vector<double> H((size_t)(d + 1) * d, 0.0), hh(2 * (d + 2)), gcs(d + 1), gsn(d + 1);
   double gres = 1.0;
-  double beta = device_norm2(c, c->eigv.p, nu);
-  k_axpby<<<nblk(nu, 256), 256, 0, c->stream>>>(nu, 1.0 / beta, c->eigv.p, 0.0, c->V.p);
+  double beta = device_norm2(c, lv.probe.p, nl);
+  k_axpby<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, 1.0 / beta, lv.probe.p, 0.0, c->V.p);
   c->launch_check();
   int dd = d;
   for (int k = 0; k < d; ++k) {
-    double* vk = c->V.p + (size_t)k * n;
-    double* w = c->V.p + (size_t)(k + 1) * n;
+    double* vk = c->V.p + (size_t)k * ld;
+    double* w = c->V.p + (size_t)(k + 1) * ld;
     const double* xin = vk;
     if (c->nranks > 1) {
-      CK(cudaMemcpyAsync(c->w_pin.p, vk, nu * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-      halo_exchange(c, c->w_pin.p, false);
-      xin = c->w_pin.p;
+      CK(cudaMemcpyAsync(lv.pin, vk, nl * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      level_halo(c, lv, lv.pin);
+      xin = lv.pin;
     }
-    spmv_vel<2>(c, xin, w, nullptr, nullptr, PolyCoef{});
+    level_apply<2>(c, lv, xin, w, nullptr, nullptr, PolyCoef{});
     for (int pass = 0; pass < 2; ++pass) {
-      k_multi_dot<<<nb, RED_THREADS, 0, c->stream>>>(k + 1, c->V.p, n, w, nu, c->partial.p);
+      k_multi_dot<<<nb, RED_THREADS, 0, c->stream>>>(k + 1, c->V.p, ld, w, nl, c->partial.p);
       c->launch_check();
       double* hp = c->d_h.p + pass * (d + 2);
       k_reduce_partials<<<k + 1, RED_THREADS, 0, c->stream>>>(nb, c->partial.p, hp, 0);
       c->launch_check();
       allreduce_sum(c, hp, k + 1);
-      k_multi_axpy<<<nb, RED_THREADS, 0, c->stream>>>(k + 1, c->V.p, n, hp, -1.0, w, nu, pass == 1 ? c->partial.p : nullptr);
+      k_multi_axpy<<<nb, RED_THREADS, 0, c->stream>>>(k + 1, c->V.p, ld, hp, -1.0, w, nl, pass == 1 ? c->partial.p : nullptr);
       c->launch_check();
     }
     k_reduce_partials<<<1, RED_THREADS, 0, c->stream>>>(nb, c->partial.p, c->d_nrm.p, 0);
     c->launch_check();
     allreduce_sum(c, c->d_nrm.p, 1);
-    k_scale_by_inv_norm<<<nblk(nu, 256), 256, 0, c->stream>>>(nu, w, c->d_nrm.p, w);
+    k_scale_by_inv_norm<<<nblk(nl, 256), 256, 0, c->stream>>>(nl, w, c->d_nrm.p, w);
     c->launch_check();
     double nrm2 = 0;
     CK(cudaMemcpyAsync(hh.data(), c->d_h.p, sizeof(double) * 2 * (d + 2), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(&nrm2, c->d_nrm.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    for (int i = 0; i <= k; ++i) H[(size_t)i * d + k] = hh[i] + hh[(d + 2) + i];
-    H[(size_t)(k + 1) * d + k] = std::sqrt(nrm2);
+    for (int i = 0; i <= k; ++i) H[(size_t)i * ldh + k] = hh[i] + hh[(d + 2) + i];
+    H[(size_t)(k + 1) * ldh + k] = std::sqrt(nrm2);
     if (!(nrm2 > 1e-28)) { dd = k + 1; break; }
     // GMRES residual of the probe vector after k+1 steps (Givens on a copy of column k)
     {
       std::vector<double> col(k + 2);
-      for (int i = 0; i <= k + 1; ++i) col[i] = H[(size_t)i * d + k];
+      for (int i = 0; i <= k + 1; ++i) col[i] = H[(size_t)i * ldh + k];
       for (int i = 0; i < k; ++i) {
         const double t = gcs[i] * col[i] + gsn[i] * col[i + 1];
         col[i + 1] = -gsn[i] * col[i] + gcs[i] * col[i + 1];
@@ -587,19 +688,17 @@ void setup_F_poly(nsb_ctx* c) {
       const double r = std::hypot(col[k], col[k + 1]);
       gcs[k] = col[k] / r; gsn[k] = col[k + 1] / r;
       gres *= std::fabs(gsn[k]);
-      if (gres <= c->opt.poly_target && k + 1 >= 2) { dd = k + 1; break; }
+      if (target > 0 && gres <= target && k + 1 >= 2) { dd = k + 1; break; }
     }
   }
-  c->poly_probe_res = gres;
+  lv.probe_res = gres;
   // harmonic Ritz values: eig(Hd + h_{d+1,d}^2 f e_d^T),  Hd^T f = e_d
   d = dd;
   std::vector<double> Hd((size_t)d * d), At((size_t)d * d), f(d, 0.0);
-  const int ldh = std::max(1, std::min(c->opt.poly_degree_F, 64));
   for (int i = 0; i < d; ++i)
     for (int j = 0; j < d; ++j) { Hd[(size_t)i * d + j] = H[(size_t)i * ldh + j]; At[(size_t)j * d + i] = H[(size_t)i * ldh + j]; }
   f[d - 1] = 1.0;
   {  // Gaussian elimination with partial pivoting on At f = e_d
-    std::vector<int> piv(d);
     for (int col = 0; col < d; ++col) {
       int p = col;
       for (int r = col + 1; r < d; ++r) if (std::fabs(At[(size_t)r * d + col]) > std::fabs(At[(size_t)p * d + col])) p = r;
@@ -613,29 +712,30 @@ void setup_F_poly(nsb_ctx* c) {
       }
     }
     for (int r = d - 1; r >= 0; --r) {
-      double s = f[r];
-      for (int k = r + 1; k < d; ++k) s -= At[(size_t)r * d + k] * f[k];
-      f[r] = s / At[(size_t)r * d + r];
+      double sum = f[r];
+      for (int k = r + 1; k < d; ++k) sum -= At[(size_t)r * d + k] * f[k];
+      f[r] = sum / At[(size_t)r * d + r];
     }
   }
   const double hl = H[(size_t)d * ldh + (d - 1)];
   for (int i = 0; i < d; ++i) Hd[(size_t)i * d + (d - 1)] += hl * hl * f[i];
-  std::vector<double> wr, wi;
-  if (!hessenberg_eigs(d, Hd, wr, wi)) throw CudaErr{"harmonic Ritz eigenvalue iteration did not converge"};
-  // Leja ordering, complex conjugates kept adjacent (positive imaginary part first)
-  std::vector<std::pair<double, double>> th, out;
-  if (c->opt.poly_kind == 1) {
-    // Chebyshev roots on the real interval spanned by the Ritz values (minimax instead of probe-optimal);
-    // only meaningful when the spectrum is essentially real
-    double lo = 1e300, hi = -1e300, im = 0;
-    for (int i = 0; i < d; ++i) { lo = std::min(lo, wr[i]); hi = std::max(hi, wr[i]); im = std::max(im, std::fabs(wi[i])); }
-    if (lo > 0 && im < 0.05 * hi) {
-      lo *= 0.9; hi *= 1.05;
-      for (int j = 1; j <= d; ++j) { wr[j - 1] = 0.5 * (hi + lo) + 0.5 * (hi - lo) * std::cos(M_PI * (2 * j - 1) / (2.0 * d)); wi[j - 1] = 0; }
-    }
+  if (!hessenberg_eigs(d, Hd, lv.wr, lv.wi)) throw CudaErr{"harmonic Ritz eigenvalue iteration did not converge"};
+  lv.ritz_lo = 1e300; lv.ritz_hi = -1e300; lv.ritz_im = 0;
+  for (int i = 0; i < d; ++i) {
+    lv.ritz_lo = std::min(lv.ritz_lo, lv.wr[i]); lv.ritz_hi = std::max(lv.ritz_hi, lv.wr[i]);
+    lv.ritz_im = std::max(lv.ritz_im, std::fabs(lv.wi[i]));
   }
+}
+
+bool level_spectrum_is_real(const PolyLevel& lv) { return lv.ritz_lo > 0 && lv.ritz_im < 0.05 * lv.ritz_hi; }
+
+// roots of the degree-d Chebyshev polynomial on [lo, hi], Leja ordered
+void set_roots(PolyLevel& lv, std::vector<double> wr, std::vector<double> wi) {
+  const int d = (int)wr.size();
+  std::vector<std::pair<double, double>> th, out;
   for (int i = 0; i < d; ++i) if (wi[i] >= 0) th.emplace_back(wr[i], wi[i]);
   auto mag = [](const std::pair<double, double>& z) { return std::hypot(z.first, z.second); };
+  // Leja ordering, complex conjugates kept adjacent (positive imaginary part first)
   while (!th.empty()) {
     size_t best = 0;
     double bv = -1e300;
@@ -654,41 +754,135 @@ void setup_F_poly(nsb_ctx* c) {
     out.push_back(th[best]);
     th.erase(th.begin() + best);
   }
-  c->poly_roots = out;
+  lv.roots = out;
+}
+void set_chebyshev_roots(PolyLevel& lv, int d, double lo, double hi) {
+  std::vector<double> wr(d), wi(d, 0.0);
+  for (int j = 1; j <= d; ++j) wr[j - 1] = 0.5 * (hi + lo) + 0.5 * (hi - lo) * std::cos(M_PI * (2 * j - 1) / (2.0 * d));
+  set_roots(lv, wr, wi);
 }
 
-// y_u = p(B) Dinv x_u  ~ F^-1 x_u ; result left in c->w_poly
-void apply_F_poly(nsb_ctx* c, const double* x) {
-  const long long nu = (long long)c->dim * c->S.nn_own;
-  double* prod = c->w_z0.p;
-  double* other = c->w_z1.p;
-  double* tmp = c->w_d.p;
-  double* poly = c->w_poly.p;
-  block_scale(c, x, prod);
-  CK(cudaMemsetAsync(poly, 0, nu * sizeof(double), c->stream));
-  const auto& R = c->poly_roots;
+// poly = p(B) z0 with p ~ B^-1 given by lv.roots in product form (Leja ordered, real arithmetic for conjugate pairs);
+// lv.z0 holds the (already Dinv-scaled) right-hand side and is destroyed; every root but the last is one fused operator
+// application.
+void apply_poly(nsb_ctx* c, PolyLevel& lv) {
+  double* prod = lv.z0;
+  double* other = lv.z1;
+  double* tmp = lv.zd;
+  double* poly = lv.poly;
+  CK(cudaMemsetAsync(poly, 0, lv.n * sizeof(double), c->stream));
+  const auto& R = lv.roots;
   for (size_t k = 0; k < R.size(); ++k) {
     const bool last = (k + 1 == R.size());
     const double a = R[k].first, b = R[k].second;
     if (b == 0.0) {
       if (last) {
-        k_axpby<<<nblk(nu, 256), 256, 0, c->stream>>>(nu, 1.0 / a, prod, 1.0, poly);
+        k_axpby<<<nblk(lv.n, 256), 256, 0, c->stream>>>(lv.n, 1.0 / a, prod, 1.0, poly);
         c->launch_check();
       } else {
         // poly += prod/theta ; prod <- prod - B prod / theta
-        halo_spmv_vel3(c, prod, other, prod, poly, PolyCoef{1.0, -1.0 / a, 1.0 / a, 0.0});
+        level_root(c, lv, prod, other, prod, poly, PolyCoef{1.0, -1.0 / a, 1.0 / a, 0.0});
         std::swap(prod, other);
       }
     } else {
       const double m2 = a * a + b * b;
       // tmp = 2a prod - B prod ; poly += tmp/m2 ; prod <- prod - B tmp / m2
-      halo_spmv_vel3(c, prod, tmp, prod, poly, PolyCoef{2.0 * a, -1.0, 0.0, 1.0 / m2});
+      level_root(c, lv, prod, tmp, prod, poly, PolyCoef{2.0 * a, -1.0, 0.0, 1.0 / m2});
       if (!last) {
-        halo_spmv_vel3(c, tmp, other, prod, poly, PolyCoef{1.0, -1.0 / m2, 0.0, 0.0});
+        level_root(c, lv, tmp, other, prod, poly, PolyCoef{1.0, -1.0 / m2, 0.0, 0.0});
         std::swap(prod, other);
       }
     }
   }
+}
+
+template <int DIM> void launch_coarse_assemble(nsb_ctx* c) {
+  Coarse& G = c->cg;
+  FeTables T;
+  fill_tables(DIM, T);
+  double wsum = 0;
+  for (int q = 0; q < T.nq; ++q) wsum += T.w[q];
+  const double gamma = c->par.use_supg ? c->par.gamma : 0.0;
+  size_t id = c->prof.begin(PC_ASM_COARSE, c->stream);
+  k_coarse_rows<DIM><<<nblk(c->S.np_own, CG_WARPS), CG_WARPS * 32, 0, c->stream>>>(c->M, c->ctx.p, gamma, wsum, G.nbr_ptr.p, G.nbr_vxoff.p,
+                                                                                     c->cflag.p, G.cvals.p, G.dinv.p);
+  c->launch_check();
+  if (c->opt.precond_precision == 16)
+    k_coarse_pack<DIM, __half><<<G.n_tiles, 256, 0, c->stream>>>(G.tiles.p, G.meta.p, G.nbr_ptr.p, G.cvals.p, G.dinv.p, reinterpret_cast<__half*>(G.vals.p));
+  else
+    k_coarse_pack<DIM, float><<<G.n_tiles, 256, 0, c->stream>>>(G.tiles.p, G.meta.p, G.nbr_ptr.p, G.cvals.p, G.dinv.p, reinterpret_cast<float*>(G.vals.p));
+  c->launch_check();
+  c->prof.end(id, c->stream);
+  G.valid = true;
+}
+
+// Rebuilds the velocity preconditioner for the currently assembled system (once per solve, or every poly_refresh-th).
+void setup_velocity_pc(nsb_ctx* c) {
+  PolyLevel& F = c->lvF;
+  bool two = c->opt.velocity_cycle != 1 && c->cg.valid && c->vs_valid;
+  if (two) {
+    // fine level: only the upper end of the spectrum of B is needed for the smoother
+    level_arnoldi(c, F, 10, 0.0);
+    two = level_spectrum_is_real(F);
+  }
+  c->two_level = two;
+  if (!two) {
+    // single level: polynomial of the degree that reduces the probe's residual below poly_target.  Real spectrum
+    // (grad-div dominated 3-D case): Chebyshev roots on the interval spanned by the harmonic Ritz values (minimax
+    // instead of probe-optimal); otherwise (convection-dominated 2-D case, Im up to 2) the harmonic Ritz values
+    // themselves -- the GMRES polynomial of Loe & Morgan -- where Chebyshev on a real interval diverges.
+    level_arnoldi(c, F, c->opt.poly_degree_F, c->opt.poly_target);
+    if (c->opt.poly_kind == 1 && level_spectrum_is_real(F)) set_chebyshev_roots(F, (int)F.wr.size(), 0.9 * F.ritz_lo, 1.05 * F.ritz_hi);
+    else set_roots(F, F.wr, F.wi);
+    return;
+  }
+  const double hi = 1.05 * F.ritz_hi;
+  set_chebyshev_roots(F, std::max(1, c->opt.smoother_degree), c->opt.smoother_lo_frac * hi, hi);
+  PolyLevel& C = c->lvC;
+  level_arnoldi(c, C, std::max(4, std::min(64, c->opt.coarse_degree + 5)), 0.05);
+  if (level_spectrum_is_real(C)) set_chebyshev_roots(C, std::max(1, c->opt.coarse_degree), 0.9 * C.ritz_lo, 1.05 * C.ritz_hi);
+  else set_roots(C, C.wr, C.wi);
+}
+
+// y_u ~ F^-1 x_u ; result left in c->w_poly
+void apply_velocity_pc(nsb_ctx* c, const double* x) {
+  PolyLevel& F = c->lvF;
+  const long long nu = F.n;
+  if (!c->two_level) {
+    level_block_scale(c, F, x, F.z0);
+    apply_poly(c, F);
+    return;
+  }
+  // ---- coarse correction  y0 = P p_c(B_c) Dinv_c P^T x
+  PolyLevel& C = c->lvC;
+  Coarse& G = c->cg;
+  const double* xr = x;
+  if (c->nranks > 1) {
+    CK(cudaMemcpyAsync(F.pin, x, nu * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    halo_exchange(c, F.pin, false);
+    xr = F.pin;
+  }
+  size_t id = c->prof.begin(PC_COARSE, c->stream);
+  if (c->dim == 2) k_restrict<2><<<nblk(c->S.np_own, 128), 128, 0, c->stream>>>(c->S.np_own, c->M.pid_node, G.vedge_ptr.p, G.vedge_xoff.p, c->cflag.p, xr, G.rc.p);
+  else k_restrict<3><<<nblk(c->S.np_own, 128), 128, 0, c->stream>>>(c->S.np_own, c->M.pid_node, G.vedge_ptr.p, G.vedge_xoff.p, c->cflag.p, xr, G.rc.p);
+  c->launch_check();
+  c->prof.end(id, c->stream);
+  level_block_scale(c, C, G.rc.p, C.z0);
+  apply_poly(c, C);
+  halo_exchange_coarse(c, C.poly);
+  double* y0 = c->w_y0.p;
+  id = c->prof.begin(PC_COARSE, c->stream);
+  if (c->dim == 2) k_prolong<2><<<nblk(nu, 256), 256, 0, c->stream>>>(c->S.nn_own, G.ends_xoff.p, c->cflag.p, C.poly, y0);
+  else k_prolong<3><<<nblk(nu, 256), 256, 0, c->stream>>>(c->S.nn_own, G.ends_xoff.p, c->cflag.p, C.poly, y0);
+  c->launch_check();
+  c->prof.end(id, c->stream);
+  // ---- smoothing from y0:  y = y0 + q(B) (Dinv x - B y0)
+  level_block_scale(c, F, x, c->w_u.p);
+  halo_exchange(c, y0, false);
+  level_apply<4>(c, F, y0, F.z0, c->w_u.p, nullptr, PolyCoef{1.0, -1.0, 0.0, 0.0});
+  apply_poly(c, F);
+  k_axpby<<<nblk(nu, 256), 256, 0, c->stream>>>(nu, 1.0, y0, 1.0, F.poly);
+  c->launch_check();
 }
 
 // ---- pressure-space pieces (global, replicated vectors of length n_p) -------------------
@@ -753,8 +947,8 @@ void precond_apply(nsb_ctx* c, const double* x, double* y) {
   const Structure& S = c->S;
   const int dim = c->dim;
   const long long nu = (long long)dim * S.nn_own;
-  // --- step 1: y0 = p(Dinv F) Dinv x0
-  apply_F_poly(c, x);
+  // --- step 1: y0 = F~^-1 x0 (two-level cycle or polynomial)
+  apply_velocity_pc(c, x);
   double* z = c->w_poly.p;
   CK(cudaMemcpyAsync(y, z, nu * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   // --- step 2: t = x1 - B y0
@@ -959,6 +1153,71 @@ void build_tiles(nsb_ctx* c) {
   else { set_smem_attr<3>(c->tile_smem_bytes); set_vs_attr<3, float>(); set_vs_attr<3, __half>(); }
 }
 
+// Coarse P1 level of the two-level velocity cycle: graph, tile / stream plans (the same builders as the fine level),
+// transfer lists, storage.  Called once per mesh, after build_tiles.
+void build_coarse_level(nsb_ctx* c) {
+  const Structure& S = c->S;
+  Coarse& G = c->cg;
+  G.built = false; G.valid = false;
+  CoarseLevel CL;
+  const std::string e = build_coarse(S, CL);
+  if (!e.empty()) throw CudaErr{e};
+  const Structure& Sc = CL.Sc;
+  for (int P = 0; P < S.np_own; ++P)
+    if (Sc.nbr_ptr[P + 1] - Sc.nbr_ptr[P] > CG_MAX_NB) throw CudaErr{"a vertex has more P1 neighbours than the coarse row kernel can accumulate"};
+  TilePlan P;
+  const TileLimits L{TILE_MAX_NODES, TILE_MAX_IDX, TILE_MAX_UNIQ, TILE_MAX_PUNIQ, VS_MAX_BLOCKS};
+  const std::string e1 = build_tile_plan(Sc, L, P);
+  if (!e1.empty()) throw CudaErr{e1};
+  VsPlan V;
+  const std::string e2 = build_vel_stream(Sc, P, V);
+  if (!e2.empty()) throw CudaErr{e2};
+  cudaStream_t st = c->stream;
+  const int dim = c->dim;
+  G.n_tiles = P.n_tiles();
+  G.total_nq = V.total_nq;
+  G.tiles.upload(V.tiles, st); G.meta.upload(V.meta, st); G.uniq_xoff.upload(P.uniq_xoff, st);
+  std::vector<long long> t64(Sc.nbr_ptr.begin(), Sc.nbr_ptr.end()), v64(CL.vedge_ptr.begin(), CL.vedge_ptr.end());
+  G.nbr_ptr.upload(t64, st); G.vedge_ptr.upload(v64, st);
+  std::vector<int> vx(Sc.nbr.size()), ex(CL.vedge.size()), en(CL.node_ends.size()), sx;
+  for (size_t i = 0; i < vx.size(); ++i) vx[i] = (int)S.node_xoff(S.pid_node[Sc.nbr[i]]);
+  for (size_t i = 0; i < ex.size(); ++i) ex[i] = (int)S.node_xoff(CL.vedge[i]);
+  for (size_t i = 0; i < en.size(); ++i) en[i] = (int)Sc.node_xoff(CL.node_ends[i]);
+  for (size_t k = 0; k < S.peer.size(); ++k)
+    for (int q : S.send_pids[k]) sx.push_back((int)Sc.node_xoff(q));
+  G.nbr_vxoff.upload(vx, st); G.vedge_xoff.upload(ex, st); G.ends_xoff.upload(en, st); G.send_xoff.upload(sx, st);
+  G.send_buf.alloc(sx.size() * dim);
+  G.gid.assign(S.pid_gid.begin(), S.pid_gid.begin() + S.np_own);
+  G.h_nbr_ptr.assign(Sc.nbr_ptr.begin(), Sc.nbr_ptr.end());
+  G.h_nbr_gid.resize(Sc.nbr.size());
+  for (size_t i = 0; i < Sc.nbr.size(); ++i) G.h_nbr_gid[i] = S.pid_gid[Sc.nbr[i]];
+  CK(cudaStreamSynchronize(st));
+  const size_t nct = (size_t)Sc.n_tot_dofs();
+  G.cvals.alloc(Sc.nbr.size() * dim * dim);
+  G.dinv.alloc((size_t)S.np_own * dim * dim);
+  for (DBuf<double>* v : {&G.rc, &G.z0, &G.z1, &G.zd, &G.poly, &G.pin}) { v->alloc(nct); v->zero(st); }
+  CK(cudaStreamSynchronize(st));
+  PolyLevel& C = c->lvC;
+  C.coarse = true; C.nn = S.np_own; C.n = (long long)dim * S.np_own; C.n_tot = (long long)nct;
+  C.dinv = G.dinv.p; C.gid = G.gid.data();
+  C.z0 = G.z0.p; C.z1 = G.z1.p; C.zd = G.zd.p; C.poly = G.poly.p; C.pin = G.pin.p;
+  C.probe_init = false; C.roots.clear();
+  G.built = true;
+}
+
+size_t coarse_vals_bytes(const nsb_ctx* c) {
+  if (c->opt.precond_precision == 64) return 0;
+  return (size_t)c->cg.total_nq * 4 * c->dim * c->dim * (c->opt.precond_precision == 16 ? 2 : 4);
+}
+
+// (re)binds the fine level of the velocity preconditioner to the context's buffers
+void bind_fine_level(nsb_ctx* c) {
+  PolyLevel& F = c->lvF;
+  F.coarse = false; F.nn = c->S.nn_own; F.n = (long long)c->dim * c->S.nn_own; F.n_tot = c->S.n_tot_dofs();
+  F.dinv = c->dinv.p; F.gid = c->S.node_gid.data();
+  F.z0 = c->w_z0.p; F.z1 = c->w_z1.p; F.zd = c->w_d.p; F.poly = c->w_poly.p; F.pin = c->w_pin.p;
+}
+
 // one-time M_p, K_p on the host over the GLOBAL P1 graph (reference cpp:798-803, 812-829)
 void host_pressure_matrices(nsb_ctx* c, const std::vector<unsigned char>& pflag) {
   const int dim = c->dim, NV = dim + 1;
@@ -1085,6 +1344,7 @@ int nsb_create(int dim, int device, nsb_handle* out) {
   c->opt.amg_smoother_degree = 2; c->opt.schur_mass_coeff = -1.0; c->opt.reorthogonalize = 1;
   c->opt.precond_precision = NSB_DEFAULT_PRECOND_PRECISION;
   c->opt.precond_operator = 1;
+  c->opt.velocity_cycle = 2; c->opt.smoother_degree = 6; c->opt.smoother_lo_frac = 0.05; c->opt.coarse_degree = 15;
   c->par.dt = 0.01; c->par.theta = 1.0; c->par.nu = 1e-3; c->par.rho = 1.0; c->par.gamma = 0.1;
   c->d_nrm.alloc(4);
   return 0;
@@ -1236,7 +1496,7 @@ int nsb_upload_mesh(nsb_handle c, int64_t n_vertices, const double* coords, int6
   // vectors and system storage
   const size_t nt = (size_t)S.n_tot_dofs();
   for (DBuf<double>* v : {&c->v_old, &c->v_oldold, &c->v_cur, &c->v_sol, &c->v_rhs, &c->cval, &c->w_z0, &c->w_z1, &c->w_d,
-                          &c->w_in, &c->w_tmp, &c->w_pin, &c->w_poly}) {
+                          &c->w_in, &c->w_tmp, &c->w_pin, &c->w_poly, &c->w_y0, &c->w_u}) {
     v->alloc(nt);
     v->zero(st);
   }
@@ -1244,13 +1504,16 @@ int nsb_upload_mesh(nsb_handle c, int64_t n_vertices, const double* coords, int6
   CK(cudaMallocHost(&c->pin, nt * sizeof(double)));
   c->cflag.alloc(nt); c->cflag.zero(st);
   c->vals.alloc((size_t)S.nnz_local);
+  build_coarse_level(c);
+  c->cg.vals.alloc(coarse_vals_bytes(c));
   c->dinv.alloc((size_t)S.nn_own * dim * dim);
   c->cell_rhs.alloc((size_t)S.nc * S.DPC);
   c->ctx_stride = 0;
   c->partial.alloc((size_t)nblk(S.n_own_dofs(), RED_CHUNK) * 4);
   CK(cudaStreamSynchronize(st));
   c->have_mesh = true; c->have_matrix = false; c->have_pressure = false;
-  c->eig_init = false; c->poly_roots.clear(); c->solves = 0; c->V_cap = 0;
+  bind_fine_level(c);
+  c->lvF.probe_init = false; c->lvF.roots.clear(); c->solves = 0; c->V_cap = 0; c->two_level = false;
   c->halo.clear();                 // pack lists of the previous mesh
   return 0;
   NSB_CATCH(c)
@@ -1354,6 +1617,10 @@ int nsb_set_solver_opts(nsb_handle c, const nsb_solver_opts* o) {
   if (n.reorthogonalize == 0) n.reorthogonalize = 1;   // 0 = default (twice); negative = a single pass
   if (n.precond_precision != 64 && n.precond_precision != 16 && n.precond_precision != 32) n.precond_precision = NSB_DEFAULT_PRECOND_PRECISION;
   n.precond_operator = 1;                         // the element-wise operator of round 1 is gone (slower than the packed copy)
+  if (n.velocity_cycle != 1 && n.velocity_cycle != 2) n.velocity_cycle = 2;
+  if (n.smoother_degree <= 0) n.smoother_degree = 6;
+  if (!(n.smoother_lo_frac > 0 && n.smoother_lo_frac < 1)) n.smoother_lo_frac = 0.05;
+  if (n.coarse_degree <= 0) n.coarse_degree = 15;
   const bool changed = n.precond_precision != c->opt.precond_precision;
   c->opt = n;
   if (c->have_mesh && changed) {
@@ -1361,10 +1628,11 @@ int nsb_set_solver_opts(nsb_handle c, const nsb_solver_opts* o) {
     try {
       cudaSetDevice(c->device);
       c->vs_vals.alloc(vs_vals_bytes(c));
-      c->vs_valid = false;
+      c->cg.vals.alloc(coarse_vals_bytes(c));
+      c->vs_valid = false; c->cg.valid = false;
     } catch (const CudaErr& e) { return fail(c, e.msg); }
     c->have_matrix = false;
-    c->poly_roots.clear();
+    c->lvF.roots.clear();
   }
   return 0;
 }
@@ -1538,7 +1806,7 @@ int nsb_solve(nsb_handle c, int max_it, double tol_rel, int n_tmp, int* iteratio
   CK(cudaSetDevice(c->device));
   int it = 0;
   double res = 0;
-  if (c->poly_roots.empty() || c->solves % c->opt.poly_refresh == 0) setup_F_poly(c);
+  if (c->lvF.roots.empty() || c->solves % c->opt.poly_refresh == 0) setup_velocity_pc(c);
   const double bnorm = device_norm2(c, c->v_rhs.p, c->S.n_own_dofs());
   const int rc = gmres(c, max_it, tol_rel * bnorm, n_tmp > 2 ? n_tmp : 150, &it, &res);
   // constraints.distribute(x)   (cpp:566, 862)
@@ -1767,10 +2035,10 @@ int nsb_solver_info(nsb_handle c, int* poly_degree, double* poly_probe_residual,
   if (!c) return -1;
   if (poly_degree) {
     int d = 0;
-    for (auto& r : c->poly_roots) d += (r.second != 0.0) ? 2 : 1;
+    for (auto& r : c->lvF.roots) d += (r.second != 0.0) ? 2 : 1;
     *poly_degree = d;
   }
-  if (poly_probe_residual) *poly_probe_residual = c->poly_probe_res;
+  if (poly_probe_residual) *poly_probe_residual = c->lvF.probe_res;
   if (amg_levels) *amg_levels = (int)c->amg.size();
   return 0;
 }
@@ -1783,6 +2051,38 @@ int nsb_velocity_operator_info(nsb_handle c, int* precision, int64_t* value_byte
   if (index_bytes) *index_bytes = 16 * c->vs_total_nq + 64 * (int64_t)c->n_stiles + 4 * (int64_t)c->d_suniq_xoff.n;
   if (tiles) *tiles = c->n_stiles;
   if (blocks) *blocks = (int64_t)c->S.nbr.size();
+  return 0;
+}
+
+int nsb_get_coarse_operator(nsb_handle c, int64_t* n_rows, int64_t* n_blocks, int64_t* row_gid, int64_t* rowptr, int64_t* col_gid,
+                            double* vals) {
+  if (!c || !c->have_mesh || !c->cg.built) return fail(c, "no coarse level");
+  NSB_TRY
+  CK(cudaSetDevice(c->device));
+  const Coarse& G = c->cg;
+  if (n_rows) *n_rows = (int64_t)G.gid.size();
+  if (n_blocks) *n_blocks = (int64_t)G.h_nbr_gid.size();
+  if (row_gid) std::copy(G.gid.begin(), G.gid.end(), row_gid);
+  if (rowptr) std::copy(G.h_nbr_ptr.begin(), G.h_nbr_ptr.end(), rowptr);
+  if (col_gid) std::copy(G.h_nbr_gid.begin(), G.h_nbr_gid.end(), col_gid);
+  if (vals) {
+    if (!G.valid) return fail(c, "the coarse operator has not been assembled (linearised systems with velocity_cycle = 2 only)");
+    CK(cudaMemcpyAsync(vals, G.cvals.p, G.cvals.n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+  NSB_CATCH(c)
+}
+
+int nsb_velocity_pc_info(nsb_handle c, int* two_level, int* smoother_degree, int* coarse_degree, int64_t* coarse_rows,
+                         int64_t* coarse_value_bytes, double* fine_lambda_max) {
+  if (!c) return -1;
+  if (two_level) *two_level = c->two_level ? 1 : 0;
+  if (smoother_degree) *smoother_degree = (int)c->lvF.roots.size();
+  if (coarse_degree) *coarse_degree = c->two_level ? (int)c->lvC.roots.size() : 0;
+  if (coarse_rows) *coarse_rows = c->lvC.n;
+  if (coarse_value_bytes) *coarse_value_bytes = (int64_t)coarse_vals_bytes(c);
+  if (fine_lambda_max) *fine_lambda_max = c->lvF.ritz_hi;
   return 0;
 }
 

@@ -537,6 +537,64 @@ int64_t verify_vel_stream(const Structure& S, const TilePlan& P, const VsPlan& V
   return bad;
 }
 
+std::string build_coarse(const Structure& S, CoarseLevel& C) {
+  C = CoarseLevel();
+  static const int lines2[3][2] = {{0, 1}, {1, 2}, {2, 0}};
+  static const int lines3[6][2] = {{0, 1}, {1, 2}, {2, 0}, {0, 3}, {1, 3}, {2, 3}};
+  const int dim = S.dim, NV = S.NV, NN = S.NN, NL = NN - NV;
+  Structure& Sc = C.Sc;
+  Sc.dim = dim; Sc.NV = NV; Sc.NN = NN; Sc.DPC = S.DPC;
+  Sc.rank = S.rank; Sc.nranks = S.nranks;
+  Sc.nn_own = S.np_own; Sc.nn_ghost = S.np_ghost; Sc.np_own = 0; Sc.np_ghost = 0; Sc.nc = 0;
+  Sc.node_gid = S.pid_gid;
+  Sc.nbr_ptr.assign(S.np_own + 1, 0);
+  for (int P = 0; P < S.np_own; ++P) {
+    const int A = S.pid_node[P];
+    Sc.nbr_ptr[P + 1] = Sc.nbr_ptr[P] + (S.pnbr_ptr[A + 1] - S.pnbr_ptr[A]);
+  }
+  Sc.nbr.resize((size_t)Sc.nbr_ptr[S.np_own]);
+  Sc.selfrank.assign(S.np_own, 0);
+  for (int P = 0; P < S.np_own; ++P) {
+    const int A = S.pid_node[P];
+    std::copy(S.pnbr.begin() + S.pnbr_ptr[A], S.pnbr.begin() + S.pnbr_ptr[A + 1], Sc.nbr.begin() + Sc.nbr_ptr[P]);
+    Sc.selfrank[P] = S.pselfrank[P];
+  }
+  Sc.pnbr_ptr.assign(S.np_own + 1, 0);
+  Sc.node_pid.assign(S.np_own + S.np_ghost, -1);
+  // halo plan of the coarse vectors = the pressure halo
+  Sc.peer = S.peer;
+  Sc.send_nodes = S.send_pids;
+  Sc.send_pids.assign(S.peer.size(), std::vector<int>());
+  Sc.recv_node_count = S.recv_pid_count;
+  Sc.recv_pid_count.assign(S.peer.size(), 0);
+  // line nodes at every owned vertex, end vertices of every owned node
+  std::vector<std::pair<int, int>> ve;
+  C.node_ends.assign((size_t)S.nn_own * 2, -1);
+  for (int c = 0; c < S.nc; ++c) {
+    const int* cn = S.cell_nodes.data() + (size_t)c * NN;
+    const int* cp = S.cell_pids.data() + (size_t)c * NV;
+    for (int v = 0; v < NV; ++v)
+      if (cn[v] < S.nn_own) { C.node_ends[2 * (size_t)cn[v]] = cp[v]; C.node_ends[2 * (size_t)cn[v] + 1] = cp[v]; }
+    for (int l = 0; l < NL; ++l) {
+      const int i = dim == 2 ? lines2[l][0] : lines3[l][0], j = dim == 2 ? lines2[l][1] : lines3[l][1];
+      const int e = cn[NV + l];
+      if (e < S.nn_own) { C.node_ends[2 * (size_t)e] = cp[i]; C.node_ends[2 * (size_t)e + 1] = cp[j]; }
+      if (cp[i] < S.np_own) ve.emplace_back(cp[i], e);
+      if (cp[j] < S.np_own) ve.emplace_back(cp[j], e);
+    }
+  }
+  for (int A = 0; A < S.nn_own; ++A)
+    if (C.node_ends[2 * (size_t)A] < 0) return "an owned node belongs to no local cell";
+  std::sort(ve.begin(), ve.end());
+  ve.erase(std::unique(ve.begin(), ve.end()), ve.end());
+  C.vedge_ptr.assign(S.np_own + 1, 0);
+  for (auto& pr : ve) C.vedge_ptr[pr.first + 1]++;
+  for (int P = 0; P < S.np_own; ++P) C.vedge_ptr[P + 1] += C.vedge_ptr[P];
+  C.vedge.resize(ve.size());
+  for (size_t k = 0; k < ve.size(); ++k) C.vedge[k] = ve[k].second;
+  return "";
+}
+
 int64_t verify_tile_plan(const Structure& S, const TileLimits& L, const TilePlan& P) {
   int64_t bad = 0;
   const int nt = P.n_tiles();

@@ -125,6 +125,19 @@ std::string build_vel_stream(const Structure& S, const TilePlan& P, VsPlan& V);
 // splits are node-aligned and monotone; returns the number of violations
 int64_t verify_vel_stream(const Structure& S, const TilePlan& P, const VsPlan& V);
 
+// Coarse level of the two-level velocity preconditioner: the P1 vector space on the mesh vertices (one coarse node per
+// pressure DoF, `dim` components each).  `Sc` describes its graph in the same form as the fine level (owned = owned
+// vertices, ghosts = ghost vertices in halo order, neighbours = the P1 stencil = pnbr of the vertex node), so the tile /
+// stream plans and kernels of the fine level serve it unchanged.  Prolongation P: a vertex node takes its coarse value, a
+// line node the mean of its two end vertices; restriction = P^T.
+struct CoarseLevel {
+  Structure Sc;
+  std::vector<int64_t> vedge_ptr;          // [np_own+1]
+  std::vector<int> vedge;                  // fine line nodes (local ids, owned or ghost) ending at each owned vertex
+  std::vector<int> node_ends;              // [nn_own][2] coarse ids of the end vertices of every owned fine node (equal for vertex nodes)
+};
+std::string build_coarse(const Structure& S, CoarseLevel& C);
+
 // Expands the local rows to scalar CSR with GLOBAL column indices, rows in local owned
 // order (velocity rows then pressure rows); for the bit-exact pattern check.
 void export_pattern(const Structure& S, std::vector<int64_t>& rowptr, std::vector<uint32_t>& col);

@@ -19,6 +19,7 @@
 //     so each finishes its rows alone (no CTA-wide barrier) with the fused epilogue:
 //         MODE 2:  y = B x                                       (Arnoldi on the scaled block)
 //         MODE 3:  y = cu*u + ct*(B x) ; poly += cpu*u + cpy*y   (one root of the polynomial in product form)
+//         MODE 4:  y = cu*u + ct*(B x)                           (scaled residual ahead of the smoother)
 //   * stages are recycled through a second mbarrier per stage (consumers -> producer); the consumer warps form two groups
 //     that take alternate tiles, so one group's block loop overlaps the other's waits and epilogue.
 //
@@ -190,7 +191,7 @@ k_vel_stream(const VsTile* __restrict__ tiles, int n_tiles, const int* __restric
     for (int q = 0; q < 2; ++q) {
       const int i = r0 + lane + 32 * q;
       pu[q] = 0.0; pp[q] = 0.0;
-      if (MODE == 3 && i < r1) { pu[q] = u[rowg0 + i]; pp[q] = poly[rowg0 + i]; }
+      if (MODE >= 3 && i < r1) { pu[q] = u[rowg0 + i]; if (MODE == 3) pp[q] = poly[rowg0 + i]; }
     }
     int carry_row = -1;
     double carry[DIM];
@@ -268,10 +269,10 @@ k_vel_stream(const VsTile* __restrict__ tiles, int n_tiles, const int* __restric
         y[rowg0 + i] = t;
       } else {
         const double uv = q == 0 ? pu[0] : q == 1 ? pu[1] : u[rowg0 + i];
-        const double pv = q == 0 ? pp[0] : q == 1 ? pp[1] : poly[rowg0 + i];
+        const double pv = MODE != 3 ? 0.0 : q == 0 ? pp[0] : q == 1 ? pp[1] : poly[rowg0 + i];
         const double yv = pc.cu * uv + pc.ct * t;
         y[rowg0 + i] = yv;
-        poly[rowg0 + i] = pv + pc.cpu * uv + pc.cpy * yv;
+        if (MODE == 3) poly[rowg0 + i] = pv + pc.cpu * uv + pc.cpy * yv;
       }
     }
     __syncwarp();

@@ -374,3 +374,113 @@ def test_streamed_velocity_operator_equals_assembled(case2d, case3d, which):
     finally:
         c.dev.set_solver_opts()
         c.linearized(0.5, False, con)
+
+
+def _p1_prolongation(mesh, dm):
+    """P1-vector -> P2-vector prolongation in the velocity numbering: vertex nodes take the vertex value, line nodes
+    the mean of their two end vertices (column index dim * vertex + component)."""
+    dim = mesh.dim
+    nv = dim + 1
+    lines = [(0, 1), (1, 2), (2, 0)] if dim == 2 else [(0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3)]
+    cd = dm.cell_dofs.astype(np.int64)
+    cells = mesh.cells.astype(np.int64)
+    rows, cols, vals = [], [], []
+    for v in range(nv):
+        for c in range(dim):
+            rows.append(cd[:, v * (dim + 1) + c]); cols.append(dim * cells[:, v] + c); vals.append(np.ones(len(cd)))
+    for l, (i, j) in enumerate(lines):
+        for c in range(dim):
+            r = cd[:, nv * (dim + 1) + dim * l + c]
+            rows += [r, r]; cols += [dim * cells[:, i] + c, dim * cells[:, j] + c]; vals += [np.full(len(cd), 0.5)] * 2
+    rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
+    _, idx = np.unique(rows * (dim * mesh.n_vertices) + cols, return_index=True)
+    return sp.csr_matrix((vals[idx], (rows[idx], cols[idx])), shape=(dm.n_u, dim * mesh.n_vertices))
+
+
+@pytest.mark.parametrize("which", ["2d", "3d"])
+def test_coarse_operator_is_the_galerkin_product(case2d, case3d, which):
+    """The coarse operator of the two-level velocity cycle, formed cell by cell from the S_ab blocks of assembly pass 1
+    (twolevel.cuh), equals P^T F P computed from the ORACLE's assembled matrix on the free coarse DoFs, and is the
+    identity on constrained ones -- in two u* regimes, with SUPG + grad-div in 3-D."""
+    c = case2d if which == "2d" else case3d
+    dim, dm, mesh = c.dim, c.dm, c.mesh
+    con = c.constraints()
+    P = _p1_prolongation(mesh, dm)
+    # coarse DoF (vertex v, comp k) is constrained iff the vertex's own velocity DoF is
+    vdof = np.zeros(dim * mesh.n_vertices, np.int64)
+    for v in range(dim + 1):
+        for k in range(dim):
+            vdof[dim * mesh.cells[:, v].astype(np.int64) + k] = dm.cell_dofs[:, v * (dim + 1) + k]
+    cfree = ~con.is_c[vdof]
+    for theta, first in ((0.5, False), (1.0, True)):
+        p = c.linearized(theta, first, con)
+        ref = asm.assemble(mesh, dm, c.pat, p, con, "linearized", c.un, c.unm1, with_pressure_matrices=False)
+        F = asm.to_csr(c.pat, ref.A, dm.n_dofs)[:dm.n_u, :dm.n_u]
+        G = (P.T @ F @ P).tocsr()
+        rg, rp, cg, v = c.dev.coarse_operator()
+        nb = np.diff(rp)
+        # pressure DoF id -> mesh vertex: pressure DoFs are numbered in vertex first-touch order = dm's vertex map
+        pvert = np.zeros(dm.n_p, np.int64)
+        for k in range(dim + 1):
+            pvert[dm.cell_dofs[:, k * (dim + 1) + dim].astype(np.int64) - dm.n_u] = mesh.cells[:, k]
+        rows_v, cols_v = pvert[np.repeat(rg, nb)], pvert[cg]
+        scale = np.abs(G).max()
+        worst = 0.0
+        for a in range(dim):
+            for b in range(dim):
+                want = np.asarray(G[dim * rows_v + a, dim * cols_v + b]).ravel()
+                fr, fc = cfree[dim * rows_v + a], cfree[dim * cols_v + b]
+                both = fr & fc
+                worst = max(worst, np.abs(v[both, a, b] - want[both]).max() / scale)
+                ident = ((rows_v == cols_v) & (a == b) & ~fr).astype(float)
+                assert np.array_equal(v[~both, a, b], ident[~both])
+        assert worst < 1e-12, worst
+        # every free-free entry of the Galerkin product lies inside the P1 pattern the kernel stores
+        Gf = sp.diags(cfree.astype(float)) @ G @ sp.diags(cfree.astype(float))
+        assert abs(Gf).sum() > 0
+        covered = sp.csr_matrix((np.ones(len(rows_v) * dim * dim),
+                                 (np.repeat(dim * rows_v, dim * dim) + np.tile(np.repeat(np.arange(dim), dim), len(rows_v)),
+                                  np.repeat(dim * cols_v, dim * dim) + np.tile(np.tile(np.arange(dim), dim), len(rows_v)))),
+                                shape=G.shape)
+        outside = Gf - Gf.multiply(covered)
+        assert abs(outside).max() < 1e-12 * scale
+
+
+def test_two_level_cycle_reaches_the_same_solution(case3d):
+    """Two-level cycle vs single-level polynomial inside the block preconditioner: different preconditioners, same linear
+    system => the same tight-tolerance solution; the cycle is selected for the linearised 3-D system and uses fewer
+    velocity-operator applications than the polynomial."""
+    c = case3d
+    nsb = c.nsb
+    con = c.constraints()
+    out = {}
+    try:
+        for cyc in (1, 2):
+            for prec in (32, 16):
+                c.dev.set_solver_opts(velocity_cycle=cyc, precond_precision=prec)
+                c.linearized(0.5, False, con)
+                c.dev.assemble_pressure_matrices()
+                c.dev.profile_enable(True)
+                c.dev.profile_reset()
+                ok, it, _ = c.dev.solve(200, 1e-2, 150)
+                napp = c.dev.profile()["spmv_vel"][1]
+                c.dev.profile_enable(False)
+                info = c.dev.velocity_pc_info()
+                assert ok and info["two_level"] == (cyc == 2), (cyc, info)
+                ok2, it2, _ = c.dev.solve(3000, 1e-12, 150)
+                assert ok2
+                out[(cyc, prec)] = (c.dev.get_vector(nsb.NSB_SOLUTION), it, napp, it2)
+        x0 = out[(1, 32)][0]
+        for k, (x, it, napp, it2) in out.items():
+            assert np.linalg.norm(x - x0) / np.linalg.norm(x0) < 1e-9, k
+        assert out[(2, 32)][2] < out[(1, 32)][2], {k: v[1:] for k, v in out.items()}
+        # bit-reproducible from solve to solve
+        c.dev.set_solver_opts()
+        c.linearized(0.5, False, con)
+        a = c.dev.solve(200, 1e-2, 150)
+        xa = c.dev.get_vector(nsb.NSB_SOLUTION)
+        b = c.dev.solve(200, 1e-2, 150)
+        assert a == b and np.array_equal(xa, c.dev.get_vector(nsb.NSB_SOLUTION))
+    finally:
+        c.dev.set_solver_opts()
+        c.linearized(0.5, False, con)
