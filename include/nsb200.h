@@ -49,7 +49,8 @@ typedef struct nsb_solver_opts {
   int32_t amg_smoother_degree; /* Chebyshev sweeps per level, pre and post  (default 2)   */
   double schur_mass_coeff;  /* coefficient of M_p^-1; <0 = theta*nu + gamma_graddiv (default),
                                set to theta*nu for the reference's exact scaling (hpp:343) */
-  int32_t reorthogonalize;  /* 0 or 1 = classical Gram-Schmidt twice (default), <0 = once  */
+  int32_t reorthogonalize;  /* 0 or 1 = classical Gram-Schmidt with a second pass when the first cancelled more than half of
+                               the vector (DGKS, default); 2 = always twice; <0 = always once */
   int32_t precond_precision;/* storage of the operator used INSIDE the velocity polynomial: a packed, tile-planar copy of
                                Dinv F in fp32 (32, default) or fp16 (16), streamed through shared memory with TMA bulk copies
                                (products and sums in fp64, so the preconditioner stays a fixed linear operator), or 64 = the
@@ -59,9 +60,10 @@ typedef struct nsb_solver_opts {
   int32_t velocity_cycle;   /* 2 (default, also 0) = two-level cycle on the velocity block of LINEARISED systems whose scaled
                                spectrum is real: P1 coarse space (Galerkin operator, Chebyshev solve) + Chebyshev smoother;
                                1 = the single-level polynomial only.  Newton systems and complex spectra always use 1. */
-  int32_t smoother_degree;  /* operator applications of the fine-level smoother per cycle      (default 6)    */
-  double smoother_lo_frac;  /* smoother interval [frac * lambda_max, lambda_max]               (default 0.05) */
+  int32_t smoother_degree;  /* operator applications of the fine-level smoother per cycle      (default 14)   */
+  double smoother_lo_frac;  /* smoother interval [frac * lambda_max, lambda_max]               (default 0.012)*/
   int32_t coarse_degree;    /* Chebyshev degree of the coarse solve                            (default 15)   */
+  double smoother_hi_factor;/* lambda_max = this factor x the largest Ritz value of 12 Arnoldi steps (default 1.1) */
 } nsb_solver_opts;
 
 /* ---- lifetime -------------------------------------------------------------------- */

