@@ -563,3 +563,62 @@ __global__ void k_gather_nodes(int n, int dim, const int* __restrict__ xoff, con
 }
 
 }  // namespace nsb
+
+// ------------------------------------------------------------------------------------
+// Halo exchange by direct peer stores (NVLink): the sender writes its boundary values into the ghost tails of the peers'
+// copies of the same vector and then raises a per-sender sequence flag in each peer; the receiver's next kernel in
+// stream order is k_halo_wait.  Replaces the Epetra Import of ghosted vectors (reference NavierStokes.cpp:561, 853,
+// 1053-1056, 1299-1300).
+// ------------------------------------------------------------------------------------
+namespace nsb {
+
+// nseg segments; segment s holds entries [seg_ptr[s], seg_ptr[s+1]) of src (offsets into v) and lands at
+// peer_vec[s % npeers] + land[s] in the peer's memory.
+__global__ void __launch_bounds__(256)
+k_halo_push(int nseg, int npeers, const int* __restrict__ seg_ptr, const int* __restrict__ src, const long long* __restrict__ land,
+            double* const* __restrict__ peer_arena, long long vec_off, const double* __restrict__ v,
+            unsigned long long* const* __restrict__ peer_flags, int my_rank, unsigned long long seq, unsigned int* counter) {
+  const int total = seg_ptr[nseg];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    int s = 0;
+    while (e >= seg_ptr[s + 1]) ++s;
+    double* dst = peer_arena[s % npeers] + vec_off + land[s] + (e - seg_ptr[s]);
+    *dst = v[src[e]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ unsigned int prev;
+  if (threadIdx.x == 0) prev = atomicAdd(counter, 1u);
+  __syncthreads();
+  if (prev == gridDim.x - 1) {
+    // every block's stores are fenced: publish the sequence number to the peers
+    __threadfence_system();
+    if (threadIdx.x < npeers) {
+      volatile unsigned long long* f = peer_flags[threadIdx.x] + my_rank;
+      *f = seq;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+    __threadfence_system();
+  }
+}
+
+// waits until every peer has written sequence number >= seq into flags[peer rank]
+__global__ void k_halo_wait(int npeers, const int* __restrict__ peer_rank, const unsigned long long* flags, unsigned long long seq) {
+  if (threadIdx.x < npeers) {
+    const volatile unsigned long long* f = flags + peer_rank[threadIdx.x];
+    while (*f < seq) { }
+  }
+  __threadfence_system();
+}
+
+// tells the peers that this rank has consumed every exchange up to `seq` (its kernels that read those ghosts precede this
+// kernel in stream order): flags[nranks + my_rank] = seq in each peer
+__global__ void k_halo_ack(int npeers, unsigned long long* const* __restrict__ peer_flags, int nranks, int my_rank, unsigned long long seq) {
+  if (threadIdx.x < npeers) {
+    volatile unsigned long long* f = peer_flags[threadIdx.x] + nranks + my_rank;
+    *f = seq;
+  }
+  __threadfence_system();
+}
+
+}  // namespace nsb

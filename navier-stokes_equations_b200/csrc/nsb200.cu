@@ -55,6 +55,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -72,12 +73,13 @@ struct NcclApi {
     CommInitRank = (decltype(CommInitRank))sym("ncclCommInitRank");
     CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
     AllReduce = (decltype(AllReduce))sym("ncclAllReduce");
+    AllGather = (decltype(AllGather))sym("ncclAllGather");
     Send = (decltype(Send))sym("ncclSend");
     Recv = (decltype(Recv))sym("ncclRecv");
     GroupStart = (decltype(GroupStart))sym("ncclGroupStart");
     GroupEnd = (decltype(GroupEnd))sym("ncclGroupEnd");
     GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
-    return GetUniqueId && CommInitRank && CommDestroy && AllReduce && Send && Recv && GroupStart && GroupEnd && GetErrorString;
+    return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather && Send && Recv && GroupStart && GroupEnd && GetErrorString;
   }
 };
 NcclApi g_nccl;
@@ -85,14 +87,21 @@ NcclApi g_nccl;
 template <typename T> struct DBuf {
   T* p = nullptr;
   size_t n = 0;
+  bool owned = true;
   DBuf() = default;
   DBuf(const DBuf&) = delete;
   DBuf& operator=(const DBuf&) = delete;
-  ~DBuf() { if (p) cudaFree(p); }
+  ~DBuf() { if (p && owned) cudaFree(p); }
   void alloc(size_t count) {
-    if (p) { cudaFree(p); p = nullptr; }
+    if (p && owned) cudaFree(p);
+    p = nullptr; owned = true;
     n = count;
     if (count) CK(cudaMalloc(&p, count * sizeof(T)));
+  }
+  // non-owning view of `count` elements at `ptr` (a slot of the symmetric halo arena)
+  void view(T* ptr, size_t count) {
+    if (p && owned) cudaFree(p);
+    p = ptr; n = count; owned = false;
   }
   void zero(cudaStream_t s) { if (n) CK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
   void upload(const std::vector<T>& v, cudaStream_t s) {
@@ -162,6 +171,32 @@ void upload_csr(const HostCsr& H, DBuf<int>& ptr, DBuf<int>& col, DBuf<double>& 
   ptr.upload(H.ptr, s); col.upload(H.col, s); val.upload(H.val, s);
   D.n = H.n; D.m = H.m; D.ptr = ptr.p; D.col = col.p; D.val = val.p;
 }
+
+// Halo exchange by direct peer stores over NVLink (no NCCL on the data path).  Every vector that is ever exchanged lives in
+// one arena per rank, at the SAME offset on every rank (slots of a common stride), exported once per mesh with
+// cudaIpcGetMemHandle; a rank therefore knows the address of "the same vector" inside each peer.  An exchange is one
+// kernel that writes the boundary values straight into the peers' ghost tails and then raises a sequence flag in each
+// peer, and one single-warp kernel that waits for the peers' flags; both are ordinary stream work.
+struct PeerHalo {
+  bool on = false;
+  DBuf<double> arena;
+  size_t stride_f = 0, stride_c = 0, coarse_base = 0;
+  int slots_f = 0, slots_c = 0;
+  DBuf<unsigned long long> flags;          // [2*nranks]: data sequence numbers, then consumed ("ack") sequence numbers
+  DBuf<unsigned int> counter;
+  std::vector<void*> opened;               // IPC mappings to close
+  std::vector<double*> peer_arena;         // per peer index (order of Structure::peer)
+  std::vector<unsigned long long*> peer_flags;
+  // device tables; segment s < npeers: velocity block for peer s, s >= npeers: pressure block for peer s - npeers
+  DBuf<double*> d_peer_arena;
+  DBuf<unsigned long long*> d_peer_flags;
+  DBuf<int> d_peer_rank;
+  DBuf<int> seg_ptr_f, src_f, seg_ptr_c, src_c;        // fine: 2*npeers segments; coarse: npeers segments
+  DBuf<long long> land_f, land_c;                      // landing offset of each segment inside the peer's vector
+  unsigned long long seq = 0;
+  const double* last_vec = nullptr;
+  int total_f_vel = 0, total_f_all = 0, total_c = 0;
+};
 
 // device view of one streamed operator (velstream.cuh)
 struct VsDev {
@@ -280,6 +315,7 @@ struct nsb_ctx {
   // preconditioner / Krylov workspace
   DBuf<double> w_z0, w_z1, w_d, w_t, w_y1, w_m0, w_m1, w_md, w_in, w_tmp, w_pin, w_poly, w_y0, w_u;
   Coarse cg;
+  PeerHalo ph;
   PolyLevel lvF, lvC;
   bool two_level = false;           // the last setup chose the two-level cycle
   DBuf<double> V;                   // Krylov basis, (m+1) vectors of n_own
@@ -322,9 +358,47 @@ size_t vs_vals_bytes(const nsb_ctx* c) {
 }
 
 // ---- halo exchange of one local vector (ghost tail refreshed from the owners) -----------
+// one exchange by peer stores: optional consumed-handshake (when the same buffer is exchanged twice in a row the peers
+// might still be reading its ghosts), push + flag, wait
+void peer_wait(nsb_ctx* c) {
+  PeerHalo& H = c->ph;
+  const int np = (int)c->S.peer.size();
+  if (np == 0) return;
+  k_halo_wait<<<1, 32, 0, c->stream>>>(np, H.d_peer_rank.p, H.flags.p, H.seq);
+  c->launch_check();
+}
+
+void peer_exchange(nsb_ctx* c, const double* v, int nseg, const DBuf<int>& seg_ptr, const DBuf<int>& src, const DBuf<long long>& land,
+                   int total_entries, bool wait = true) {
+  PeerHalo& H = c->ph;
+  const int np = (int)c->S.peer.size();
+  if (np == 0) return;
+  const long long vec_off = v - H.arena.p;
+  if (vec_off < 0 || (size_t)vec_off >= H.arena.n) throw CudaErr{"halo exchange of a vector outside the symmetric arena"};
+  if (v == H.last_vec) {
+    k_halo_ack<<<1, 32, 0, c->stream>>>(np, H.d_peer_flags.p, c->nranks, c->rank, H.seq);
+    c->launch_check();
+    k_halo_wait<<<1, 32, 0, c->stream>>>(np, H.d_peer_rank.p, H.flags.p + c->nranks, H.seq);
+    c->launch_check();
+  }
+  H.last_vec = v;
+  ++H.seq;
+  const int grid = std::max(1, std::min(nblk(total_entries, 256), 64));
+  k_halo_push<<<grid, 256, 0, c->stream>>>(nseg, np, seg_ptr.p, src.p, land.p, H.d_peer_arena.p, vec_off, v, H.d_peer_flags.p, c->rank,
+                                            H.seq, H.counter.p);
+  c->launch_check();
+  if (wait) peer_wait(c);
+}
+
 void halo_exchange(nsb_ctx* c, double* v, bool with_pressure = true) {
   if (c->nranks == 1) return;
   const Structure& S = c->S;
+  if (c->ph.on) {
+    const int np = (int)S.peer.size();
+    const int nseg = with_pressure ? 2 * np : np;
+    peer_exchange(c, v, nseg, c->ph.seg_ptr_f, c->ph.src_f, c->ph.land_f, with_pressure ? c->ph.total_f_all : c->ph.total_f_vel);
+    return;
+  }
   // One pack kernel for all peers (+ one for the pressure DoFs), then a grouped send/recv: ghosts are stored per
   // owner contiguously, so receives land in place.  The velocity polynomial only needs velocity ghosts.
   auto& B = c->halo;
@@ -507,10 +581,12 @@ void halo_spmv_vel3(nsb_ctx* c, double* x, double* y, const double* u, double* p
     spmv_vel<3>(c, x, y, u, poly, pc);
     return;
   }
-  halo_start_velocity(c, x);
+  if (c->ph.on) peer_exchange(c, x, (int)c->S.peer.size(), c->ph.seg_ptr_f, c->ph.src_f, c->ph.land_f, c->ph.total_f_vel, false);
+  else halo_start_velocity(c, x);
   size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
   vel_stream<3, true>(c, fine_dev(c), c->n_tiles_int, c->d_tiles_int.p, x, y, u, poly, pc);
-  CK(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+  if (c->ph.on) peer_wait(c);
+  else CK(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
   vel_stream<3, true>(c, fine_dev(c), c->n_tiles_bnd, c->d_tiles_bnd.p, x, y, u, poly, pc);
   c->prof.end(id, c->stream);
 }
@@ -568,6 +644,10 @@ VsDev coarse_dev(const nsb_ctx* c) {
 void halo_exchange_coarse(nsb_ctx* c, double* v) {
   if (c->nranks == 1) return;
   const Structure& S = c->S;
+  if (c->ph.on) {
+    peer_exchange(c, v, (int)S.peer.size(), c->ph.seg_ptr_c, c->ph.src_c, c->ph.land_c, c->ph.total_c);
+    return;
+  }
   Coarse& G = c->cg;
   const int dim = c->dim;
   const long long tp = (long long)G.send_xoff.n;
@@ -649,9 +729,10 @@ void level_arnoldi(nsb_ctx* c, PolyLevel& lv, int dmax, double target) {
     double* w = c->V.p + (size_t)(k + 1) * ld;
     const double* xin = vk;
     if (c->nranks > 1) {
-      CK(cudaMemcpyAsync(lv.pin, vk, nl * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-      level_halo(c, lv, lv.pin);
-      xin = lv.pin;
+      double* buf = (k & 1) ? lv.z1 : lv.pin;       // never the same buffer twice in a row (peer-store halo)
+      CK(cudaMemcpyAsync(buf, vk, nl * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      level_halo(c, lv, buf);
+      xin = buf;
     }
     level_apply<2>(c, lv, xin, w, nullptr, nullptr, PolyCoef{});
     for (int pass = 0; pass < 2; ++pass) {
@@ -866,9 +947,9 @@ void apply_velocity_pc(nsb_ctx* c, const double* x) {
   Coarse& G = c->cg;
   const double* xr = x;
   if (c->nranks > 1) {
-    CK(cudaMemcpyAsync(F.pin, x, nu * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    halo_exchange(c, F.pin, false);
-    xr = F.pin;
+    CK(cudaMemcpyAsync(c->w_u.p, x, nu * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));      // (w_u is rewritten below)
+    halo_exchange(c, c->w_u.p, false);
+    xr = c->w_u.p;
   }
   size_t id = c->prof.begin(PC_COARSE, c->stream);
   if (c->dim == 2) k_restrict<2><<<nblk(c->S.np_own, 128), 128, 0, c->stream>>>(c->S.np_own, c->M.pid_node, G.vedge_ptr.p, G.vedge_xoff.p, c->cflag.p, xr, G.rc.p);
@@ -1173,6 +1254,141 @@ void build_tiles(nsb_ctx* c) {
   else { set_smem_attr<3>(c->tile_smem_bytes); set_vs_attr<3, float>(); set_vs_attr<3, __half>(); }
 }
 
+void close_peer_halo(nsb_ctx* c) {
+  PeerHalo& H = c->ph;
+  for (void* q : H.opened) cudaIpcCloseMemHandle(q);
+  H.opened.clear(); H.peer_arena.clear(); H.peer_flags.clear();
+  H.on = false;
+}
+
+void nccl_barrier(nsb_ctx* c) {
+  if (c->nranks == 1 || !c->comm) return;
+  CKN(g_nccl.AllReduce(c->d_nrm.p + 2, c->d_nrm.p + 2, 1, ncclDouble, ncclSum, c->comm, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+}
+
+// All vectors that take part in halo exchanges as views into one symmetric arena (see PeerHalo); called from
+// nsb_upload_mesh on several ranks, before the vectors are used.  `fine` / `coarse` = the buffers to place.
+void setup_peer_halo(nsb_ctx* c, std::vector<DBuf<double>*> fine, std::vector<DBuf<double>*> coarse, size_t nt, size_t nct) {
+  PeerHalo& H = c->ph;
+  const Structure& S = c->S;
+  const int R = c->nranks, dim = c->dim, np = (int)S.peer.size();
+  cudaStream_t st = c->stream;
+  close_peer_halo(c);
+  nccl_barrier(c);                                   // nobody still maps the arena that is about to be freed
+  // common strides
+  long long hs[2] = {(long long)nt, (long long)nct};
+  DBuf<long long> ds;
+  ds.alloc(2);
+  CK(cudaMemcpyAsync(ds.p, hs, sizeof(hs), cudaMemcpyHostToDevice, st));
+  CKN(g_nccl.AllReduce(ds.p, ds.p, 2, ncclInt64, ncclMax, c->comm, st));
+  CK(cudaMemcpyAsync(hs, ds.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  H.stride_f = ((size_t)hs[0] + 31) / 32 * 32;
+  H.stride_c = ((size_t)hs[1] + 31) / 32 * 32;
+  H.slots_f = (int)fine.size(); H.slots_c = (int)coarse.size();
+  H.coarse_base = H.stride_f * H.slots_f;
+  H.arena.alloc(H.coarse_base + H.stride_c * H.slots_c);
+  H.arena.zero(st);
+  for (size_t i = 0; i < fine.size(); ++i) fine[i]->view(H.arena.p + i * H.stride_f, nt);
+  for (size_t i = 0; i < coarse.size(); ++i) coarse[i]->view(H.arena.p + H.coarse_base + i * H.stride_c, nct);
+  H.flags.alloc(2 * (size_t)R); H.flags.zero(st);
+  H.counter.alloc(1); H.counter.zero(st);
+  H.seq = 0; H.last_vec = nullptr;
+  const char* mode = std::getenv("NSB200_HALO");
+  const bool want = !(mode && std::string(mode) == "nccl");
+  // where each peer's data lands in MY vectors: [r][0] velocity, [r][1] pressure, [r][2] coarse; gathered so that every
+  // sender can look up its landing offsets in the receivers' tables
+  std::vector<long long> mine((size_t)R * 3, -1), all((size_t)R * R * 3, -1);
+  {
+    long long uoff = S.n_own_dofs(), poff = S.n_own_dofs() + (long long)dim * S.nn_ghost, coff = (long long)dim * S.np_own;
+    for (int k = 0; k < np; ++k) {
+      mine[(size_t)S.peer[k] * 3 + 0] = uoff; mine[(size_t)S.peer[k] * 3 + 1] = poff; mine[(size_t)S.peer[k] * 3 + 2] = coff;
+      uoff += (long long)S.recv_node_count[k] * dim; poff += S.recv_pid_count[k]; coff += (long long)S.recv_pid_count[k] * dim;
+    }
+  }
+  struct Handles { cudaIpcMemHandle_t arena, flags; };
+  Handles hm;
+  std::vector<Handles> hall(R);
+  bool ok = want;
+  if (ok) ok = cudaIpcGetMemHandle(&hm.arena, H.arena.p) == cudaSuccess && cudaIpcGetMemHandle(&hm.flags, H.flags.p) == cudaSuccess;
+  if (!ok) { std::memset(&hm, 0, sizeof(hm)); cudaGetLastError(); }
+  {
+    DBuf<unsigned char> g0, g1;
+    DBuf<long long> t0, t1;
+    g0.alloc(sizeof(Handles) + 8); g1.alloc((sizeof(Handles) + 8) * R);
+    t0.alloc(mine.size()); t1.alloc(all.size());
+    unsigned char pack[sizeof(Handles) + 8] = {0};
+    std::memcpy(pack, &hm, sizeof(hm));
+    pack[sizeof(Handles)] = ok ? 1 : 0;
+    CK(cudaMemcpyAsync(g0.p, pack, sizeof(pack), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(t0.p, mine.data(), mine.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CKN(g_nccl.AllGather(g0.p, g1.p, sizeof(pack), ncclChar, c->comm, st));
+    CKN(g_nccl.AllGather(t0.p, t1.p, mine.size(), ncclInt64, c->comm, st));
+    std::vector<unsigned char> back((sizeof(Handles) + 8) * R);
+    CK(cudaMemcpyAsync(back.data(), g1.p, back.size(), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(all.data(), t1.p, all.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int r = 0; r < R; ++r) {
+      std::memcpy(&hall[r], back.data() + (sizeof(Handles) + 8) * r, sizeof(Handles));
+      ok = ok && back[(sizeof(Handles) + 8) * r + sizeof(Handles)] == 1;      // every rank must be able to export
+    }
+  }
+  if (ok) {
+    for (int k = 0; k < np && ok; ++k) {
+      void *pa = nullptr, *pf = nullptr;
+      ok = cudaIpcOpenMemHandle(&pa, hall[S.peer[k]].arena, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      if (ok) { H.opened.push_back(pa); ok = cudaIpcOpenMemHandle(&pf, hall[S.peer[k]].flags, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess; }
+      if (ok) H.opened.push_back(pf);
+      H.peer_arena.push_back((double*)pa); H.peer_flags.push_back((unsigned long long*)pf);
+    }
+    if (!ok) cudaGetLastError();
+  }
+  // the decision must be unanimous: one more reduction over "all my mappings opened"
+  {
+    DBuf<long long> d;
+    d.alloc(1);
+    long long v = ok ? 1 : 0;
+    CK(cudaMemcpyAsync(d.p, &v, sizeof(v), cudaMemcpyHostToDevice, st));
+    CKN(g_nccl.AllReduce(d.p, d.p, 1, ncclInt64, ncclMin, c->comm, st));
+    CK(cudaMemcpyAsync(&v, d.p, sizeof(v), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ok = v == 1;
+  }
+  if (!ok) {
+    if (want && c->rank == 0) std::fprintf(stderr, "nsb200: peer-store halo unavailable (CUDA IPC), using NCCL send/recv\n");
+    close_peer_halo(c);
+    return;
+  }
+  // segments
+  std::vector<int> sp(1, 0), src, spc(1, 0), srcc, pr(np);
+  std::vector<long long> land(2 * (size_t)np), landc(np);
+  for (int k = 0; k < np; ++k) {
+    pr[k] = S.peer[k];
+    for (int n : S.send_nodes[k]) for (int cc = 0; cc < dim; ++cc) src.push_back((int)S.node_xoff(n) + cc);
+    sp.push_back((int)src.size());
+    land[k] = all[((size_t)S.peer[k] * R + c->rank) * 3 + 0];
+  }
+  H.total_f_vel = (int)src.size();
+  for (int k = 0; k < np; ++k) {
+    for (int q : S.send_pids[k]) src.push_back((int)S.pid_xoff(q));
+    sp.push_back((int)src.size());
+    land[np + k] = all[((size_t)S.peer[k] * R + c->rank) * 3 + 1];
+    for (int q : S.send_pids[k]) for (int cc = 0; cc < dim; ++cc) srcc.push_back(dim * q + cc);
+    spc.push_back((int)srcc.size());
+    landc[k] = all[((size_t)S.peer[k] * R + c->rank) * 3 + 2];
+  }
+  H.total_f_all = (int)src.size(); H.total_c = (int)srcc.size();
+  for (int k = 0; k < np; ++k)
+    if (land[k] < 0 || land[np + k] < 0 || landc[k] < 0) throw CudaErr{"halo plan mismatch: a peer does not expect data from this rank"};
+  H.seg_ptr_f.upload(sp, st); H.src_f.upload(src, st); H.land_f.upload(land, st);
+  H.seg_ptr_c.upload(spc, st); H.src_c.upload(srcc, st); H.land_c.upload(landc, st);
+  H.d_peer_arena.upload(H.peer_arena, st); H.d_peer_flags.upload(H.peer_flags, st); H.d_peer_rank.upload(pr, st);
+  CK(cudaStreamSynchronize(st));
+  nccl_barrier(c);                                   // every rank's flags are zeroed before anybody pushes
+  H.on = true;
+}
+
 // Coarse P1 level of the two-level velocity cycle: graph, tile / stream plans (the same builders as the fine level),
 // transfer lists, storage.  Called once per mesh, after build_tiles.
 void build_coarse_level(nsb_ctx* c) {
@@ -1215,7 +1431,13 @@ void build_coarse_level(nsb_ctx* c) {
   const size_t nct = (size_t)Sc.n_tot_dofs();
   G.cvals.alloc(Sc.nbr.size() * dim * dim);
   G.dinv.alloc((size_t)S.np_own * dim * dim);
-  for (DBuf<double>* v : {&G.rc, &G.z0, &G.z1, &G.zd, &G.poly, &G.pin}) { v->alloc(nct); v->zero(st); }
+  if (c->nranks == 1) {
+    for (DBuf<double>* v : {&G.rc, &G.z0, &G.z1, &G.zd, &G.poly, &G.pin}) { v->alloc(nct); v->zero(st); }
+  } else {
+    setup_peer_halo(c, {&c->v_old, &c->v_oldold, &c->v_cur, &c->v_sol, &c->v_rhs, &c->cval, &c->w_z0, &c->w_z1, &c->w_d, &c->w_in, &c->w_tmp,
+                        &c->w_pin, &c->w_poly, &c->w_y0, &c->w_u},
+                    {&G.rc, &G.z0, &G.z1, &G.zd, &G.poly, &G.pin}, (size_t)S.n_tot_dofs(), nct);
+  }
   CK(cudaStreamSynchronize(st));
   PolyLevel& C = c->lvC;
   C.coarse = true; C.nn = S.np_own; C.n = (long long)dim * S.np_own; C.n_tot = (long long)nct;
@@ -1375,6 +1597,10 @@ int nsb_destroy(nsb_handle c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->ph.on) {
+    // peers may still map this rank's arena: close our mappings, then rendezvous before anything is freed
+    try { close_peer_halo(c); nccl_barrier(c); } catch (...) {}
+  }
   if (c->comm_stream) { cudaStreamSynchronize(c->comm_stream); cudaStreamDestroy(c->comm_stream); }
   if (c->ev_pack) cudaEventDestroy(c->ev_pack);
   if (c->ev_halo) cudaEventDestroy(c->ev_halo);
@@ -1513,18 +1739,20 @@ int nsb_upload_mesh(nsb_handle c, int64_t n_vertices, const double* coords, int6
     c->w_gather.alloc((size_t)(n_u + n_p));
     CK(cudaStreamSynchronize(st));
   }
-  // vectors and system storage
+  // vectors and system storage (several ranks: build_coarse_level places all exchanged vectors in the symmetric arena)
   const size_t nt = (size_t)S.n_tot_dofs();
-  for (DBuf<double>* v : {&c->v_old, &c->v_oldold, &c->v_cur, &c->v_sol, &c->v_rhs, &c->cval, &c->w_z0, &c->w_z1, &c->w_d,
-                          &c->w_in, &c->w_tmp, &c->w_pin, &c->w_poly, &c->w_y0, &c->w_u}) {
-    v->alloc(nt);
-    v->zero(st);
+  build_coarse_level(c);
+  if (c->nranks == 1) {
+    for (DBuf<double>* v : {&c->v_old, &c->v_oldold, &c->v_cur, &c->v_sol, &c->v_rhs, &c->cval, &c->w_z0, &c->w_z1, &c->w_d,
+                            &c->w_in, &c->w_tmp, &c->w_pin, &c->w_poly, &c->w_y0, &c->w_u}) {
+      v->alloc(nt);
+      v->zero(st);
+    }
   }
   if (c->pin) { cudaFreeHost(c->pin); c->pin = nullptr; }
   CK(cudaMallocHost(&c->pin, nt * sizeof(double)));
   c->cflag.alloc(nt); c->cflag.zero(st);
   c->vals.alloc((size_t)S.nnz_local);
-  build_coarse_level(c);
   c->cg.vals.alloc(coarse_vals_bytes(c));
   c->dinv.alloc((size_t)S.nn_own * dim * dim);
   c->cell_rhs.alloc((size_t)S.nc * S.DPC);
