@@ -52,7 +52,7 @@ typedef struct nsb_solver_opts {
   int32_t reorthogonalize;  /* 0 or 1 = classical Gram-Schmidt with a second pass when the first cancelled more than half of
                                the vector (DGKS, default); 2 = always twice; <0 = always once */
   int32_t precond_precision;/* storage of the operator used INSIDE the velocity polynomial: a packed, tile-planar copy of
-                               Dinv F in fp32 (32, default) or fp16 (16), streamed through shared memory with TMA bulk copies
+                               Dinv F in fp16 (16, default) or fp32 (32), streamed through shared memory with TMA bulk copies
                                (products and sums in fp64, so the preconditioner stays a fixed linear operator), or 64 = the
                                assembled fp64 values themselves.  Changing it invalidates the assembled system
                                (re-assemble before solving). */
@@ -168,6 +168,9 @@ int nsb_solver_info(nsb_handle h, int* poly_degree, double* poly_probe_residual,
  * array, bytes of its index side (block metadata, tile headers, unique-neighbour lists), tiles, (node, neighbour) blocks */
 int nsb_velocity_operator_info(nsb_handle h, int* precision, int64_t* value_bytes, int64_t* index_bytes, int64_t* tiles,
                                int64_t* blocks);
+/* how the ghost entries travel: halo_mode 0 = single GPU, 1 = NCCL send/recv, 2 = peer stores over NVLink (CUDA IPC; separate
+ * push / wait kernels), 3 = peer stores fused into the streamed velocity operator; doubles this rank sends per velocity exchange */
+int nsb_comm_info(nsb_handle h, int* nranks, int* halo_mode, int64_t* halo_doubles_per_exchange);
 /* inspection (parity tests): the Galerkin coarse operator P^T F P of the two-level velocity cycle as block CSR over the owned
  * vertices -- global vertex id of every row, block row pointer, global vertex id of every block column, dim*dim values per
  * block (row-major).  NULL arrays are skipped (call once for the sizes). */

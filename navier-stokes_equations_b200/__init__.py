@@ -265,6 +265,13 @@ class Device:
         self._ck(lib().nsb_get_coarse_operator(self.h, C.byref(n), C.byref(nb), _p(rg, C.c_int64), _p(rp, C.c_int64), _p(cg, C.c_int64), _p(v, C.c_double)))
         return rg, rp, cg, v
 
+    def comm_info(self):
+        a, b = C.c_int(), C.c_int()
+        d = C.c_int64()
+        self._ck(lib().nsb_comm_info(self.h, C.byref(a), C.byref(b), C.byref(d)))
+        return dict(nranks=a.value, halo=("none", "nccl send/recv", "peer stores over NVLink (CUDA IPC)", "peer stores fused into the streamed operator")[b.value],
+                    halo_doubles_per_exchange=d.value)
+
     def velocity_pc_info(self):
         a, b, d = C.c_int(), C.c_int(), C.c_int()
         r, v = C.c_int64(), C.c_int64()

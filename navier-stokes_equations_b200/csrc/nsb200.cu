@@ -196,6 +196,13 @@ struct PeerHalo {
   unsigned long long seq = 0;
   const double* last_vec = nullptr;
   int total_f_vel = 0, total_f_all = 0, total_c = 0;
+  // fused delivery inside the streamed operator (VsHalo): per owned node / vertex the peers' landing offsets, the tile lists
+  // [tiles without ghost reads | tiles with], and which vector currently has a delivery in flight
+  DBuf<int> send_ptr_f, send_ptr_c, list_f, list_c;
+  DBuf<int2> send_dst_f, send_dst_c;
+  int n_int_f = 0, n_int_c = 0;
+  const double* fresh_vec = nullptr;       // its ghosts are being delivered by the kernel that produced it ...
+  unsigned long long fresh_seq = 0;        // ... under this sequence number
 };
 
 // device view of one streamed operator (velstream.cuh)
@@ -233,6 +240,7 @@ struct Coarse {
   DBuf<long long> nbr_ptr, vedge_ptr;
   DBuf<int> nbr_vxoff, vedge_xoff, ends_xoff, send_xoff;
   DBuf<double> cvals, dinv, rc, z0, z1, zd, poly, pin, send_buf;
+  std::vector<int> h_tiles_int, h_tiles_bnd, h_tile_node_ptr;
   std::vector<int64_t> gid, h_nbr_ptr, h_nbr_gid;     // host copies: global vertex ids of the owned rows / of the neighbours
   bool built = false, valid = false;   // structures uploaded / operator matches the assembled system
 };
@@ -308,7 +316,10 @@ struct nsb_ctx {
   cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;
   DBuf<int> d_tiles_int, d_tiles_bnd;
   int n_tiles_int = 0, n_tiles_bnd = 0;
+  std::vector<int> h_tiles_int, h_tiles_bnd, h_tile_node_ptr;     // host copies (fused halo tables)
   bool overlap = false;
+  bool fused_halo = false;          // halo exchange fused into the streamed operator (peer-store halo only): NSB200_FUSED_HALO=1.
+                                    // Off by default: measured 4-5 % slower than the separate push / wait kernels on 2 GPUs (profiles/README.md)
   double* pin = nullptr;           // pinned staging buffer for host <-> device vector traffic (n_tot doubles)
   DBuf<double> coarse_inv;
   int coarse_n = 0;
@@ -348,7 +359,7 @@ int fail(nsb_ctx* c, const std::string& m, int code = -1) {
 inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 
 #ifndef NSB_DEFAULT_PRECOND_PRECISION
-#define NSB_DEFAULT_PRECOND_PRECISION 32
+#define NSB_DEFAULT_PRECOND_PRECISION 16
 #endif
 
 // bytes of the packed copy of Dinv F (none when the polynomial runs on the fp64 values themselves)
@@ -382,6 +393,7 @@ void peer_exchange(nsb_ctx* c, const double* v, int nseg, const DBuf<int>& seg_p
     c->launch_check();
   }
   H.last_vec = v;
+  H.fresh_vec = nullptr;
   ++H.seq;
   const int grid = std::max(1, std::min(nblk(total_entries, 256), 64));
   k_halo_push<<<grid, 256, 0, c->stream>>>(nseg, np, seg_ptr.p, src.p, land.p, H.d_peer_arena.p, vec_off, v, H.d_peer_flags.p, c->rank,
@@ -433,31 +445,6 @@ void halo_exchange(nsb_ctx* c, double* v, bool with_pressure = true) {
     su += nu; sp += np;
   }
   CKN(g_nccl.GroupEnd());
-}
-
-// velocity-only exchange started on the communication stream; the caller waits on ev_halo before it reads ghosts
-void halo_start_velocity(nsb_ctx* c, double* v) {
-  const Structure& S = c->S;
-  if (c->halo.empty()) { halo_exchange(c, v, false); CK(cudaEventRecord(c->ev_halo, c->stream)); return; }   // builds the pack lists
-  HaloBuf& H = *c->halo[0];
-  const long long tu = (long long)H.uoff.n;
-  if (tu) { k_gather_nodes<<<nblk(tu * S.dim, 256), 256, 0, c->stream>>>((int)tu, S.dim, H.uoff.p, v, H.u.p); c->launch_check(); }
-  CK(cudaEventRecord(c->ev_pack, c->stream));
-  CK(cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
-  CKN(g_nccl.GroupStart());
-  long long uoff = S.n_own_dofs();
-  size_t su = 0;
-  for (size_t k = 0; k < S.peer.size(); ++k) {
-    const int peer = S.peer[k];
-    const size_t nu = S.send_nodes[k].size() * S.dim;
-    if (nu) CKN(g_nccl.Send(H.u.p + su, nu, ncclDouble, peer, c->comm, c->comm_stream));
-    const size_t ru = (size_t)S.recv_node_count[k] * S.dim;
-    if (ru) CKN(g_nccl.Recv(v + uoff, ru, ncclDouble, peer, c->comm, c->comm_stream));
-    uoff += ru;
-    su += nu;
-  }
-  CKN(g_nccl.GroupEnd());
-  CK(cudaEventRecord(c->ev_halo, c->comm_stream));
 }
 
 void allreduce_sum(nsb_ctx* c, double* dbuf, int n) {
@@ -525,26 +512,29 @@ template <int DIM, typename VT> void set_vs_attr() {
   CK(cudaFuncSetAttribute(k_vel_stream<DIM, VT, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute(k_vel_stream<DIM, VT, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute(k_vel_stream<DIM, VT, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CK(cudaFuncSetAttribute(k_vel_stream<DIM, VT, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 }
 
 // one application of the streamed operator over `ntiles` tiles (all of them, or the listed ones)
-template <int DIM, typename VT, int MODE, bool LISTED>
-void launch_vel_stream(nsb_ctx* c, const VsDev& D, int ntiles, const int* list, const double* x, double* y, const double* u, double* poly, PolyCoef pc) {
+template <int DIM, typename VT, int MODE, bool HALO>
+void launch_vel_stream(nsb_ctx* c, const VsDev& D, int ntiles, const int* list, const double* x, double* y, const double* u, double* poly,
+                       PolyCoef pc, const VsHalo& hx) {
   if (ntiles <= 0) return;
   const int grid = std::min(ntiles, c->num_sms);
-  k_vel_stream<DIM, VT, MODE, LISTED><<<grid, VS_THREADS, VsLayout<DIM, VT>::SMEM_BYTES, c->stream>>>(
-      D.tiles, ntiles, list, reinterpret_cast<const VT*>(D.vals), D.meta, D.uniq_xoff, x, y, u, poly, pc);
+  k_vel_stream<DIM, VT, MODE, HALO><<<grid, VS_THREADS, VsLayout<DIM, VT>::SMEM_BYTES, c->stream>>>(
+      D.tiles, ntiles, list, reinterpret_cast<const VT*>(D.vals), D.meta, D.uniq_xoff, x, y, u, poly, pc, hx);
   c->launch_check();
 }
-template <int MODE, bool LISTED>
-void vel_stream(nsb_ctx* c, const VsDev& D, int ntiles, const int* list, const double* x, double* y, const double* u, double* poly, PolyCoef pc) {
+template <int MODE, bool HALO>
+void vel_stream(nsb_ctx* c, const VsDev& D, int ntiles, const int* list, const double* x, double* y, const double* u, double* poly, PolyCoef pc,
+                const VsHalo& hx = VsHalo{}) {
   const bool h = c->opt.precond_precision == 16;
   if (c->dim == 2) {
-    if (h) launch_vel_stream<2, __half, MODE, LISTED>(c, D, ntiles, list, x, y, u, poly, pc);
-    else launch_vel_stream<2, float, MODE, LISTED>(c, D, ntiles, list, x, y, u, poly, pc);
+    if (h) launch_vel_stream<2, __half, MODE, HALO>(c, D, ntiles, list, x, y, u, poly, pc, hx);
+    else launch_vel_stream<2, float, MODE, HALO>(c, D, ntiles, list, x, y, u, poly, pc, hx);
   } else {
-    if (h) launch_vel_stream<3, __half, MODE, LISTED>(c, D, ntiles, list, x, y, u, poly, pc);
-    else launch_vel_stream<3, float, MODE, LISTED>(c, D, ntiles, list, x, y, u, poly, pc);
+    if (h) launch_vel_stream<3, __half, MODE, HALO>(c, D, ntiles, list, x, y, u, poly, pc, hx);
+    else launch_vel_stream<3, float, MODE, HALO>(c, D, ntiles, list, x, y, u, poly, pc, hx);
   }
 }
 VsDev fine_dev(const nsb_ctx* c);
@@ -572,23 +562,48 @@ void spmv_vel(nsb_ctx* c, const double* x, double* y, const double* u, double* p
   c->prof.end(id, c->stream);
 }
 
-// one root of the velocity polynomial on a vector whose ghosts are stale: exchange + operator application; with
-// NSB200_OVERLAP=1 the tiles that read no ghost entry run while the exchange is in flight, the boundary tiles after it
+// Operator application with the halo exchange fused into the streamed kernel (VsHalo, velstream.cuh): x's ghosts are either
+// already being delivered by the kernel that produced x (then this kernel waits for the peers' flags itself, behind its
+// interior tiles) or are exchanged by the separate push / wait kernels first; y's boundary rows are delivered to the peers
+// by this kernel.  MODE 3 or 4.
+template <int MODE>
+void fused_apply(nsb_ctx* c, bool coarse, const VsDev& D, double* x, double* y, const double* u, double* poly, PolyCoef pc) {
+  PeerHalo& H = c->ph;
+  const int np = (int)c->S.peer.size();
+  VsHalo hx{};
+  hx.flags = H.flags.p; hx.peer_rank = H.d_peer_rank.p; hx.npeers = np;
+  hx.n_int = coarse ? H.n_int_c : H.n_int_f;
+  hx.ghost_start = coarse ? c->dim * c->S.np_own : (int)c->S.n_own_dofs();
+  if (x == H.fresh_vec) hx.wait_seq = H.fresh_seq;
+  else {
+    if (coarse) peer_exchange(c, x, np, H.seg_ptr_c, H.src_c, H.land_c, H.total_c);
+    else peer_exchange(c, x, np, H.seg_ptr_f, H.src_f, H.land_f, H.total_f_vel);
+    hx.wait_seq = 0;
+  }
+  hx.send_ptr = coarse ? H.send_ptr_c.p : H.send_ptr_f.p;
+  hx.send_dst = coarse ? H.send_dst_c.p : H.send_dst_f.p;
+  hx.peer_arena = H.d_peer_arena.p;
+  hx.y_off = y - H.arena.p;
+  if (hx.y_off < 0 || (size_t)hx.y_off >= H.arena.n) throw CudaErr{"fused halo delivery into a vector outside the symmetric arena"};
+  hx.peer_flags = H.d_peer_flags.p; hx.my_rank = c->rank;
+  hx.push_seq = ++H.seq;
+  hx.counter = H.counter.p;
+  const int* list = coarse ? H.list_c.p : H.list_f.p;
+  vel_stream<MODE, true>(c, D, D.n_tiles, list, x, y, u, poly, pc, hx);
+  H.fresh_vec = y; H.fresh_seq = hx.push_seq;
+  H.last_vec = nullptr;
+}
+
+// one root of the velocity polynomial on a vector whose ghosts are stale
 void halo_spmv_vel3(nsb_ctx* c, double* x, double* y, const double* u, double* poly, PolyCoef pc) {
-  const bool ovl = c->nranks > 1 && c->overlap && c->vs_valid && c->n_tiles_int > 0;
-  if (!ovl) {
-    halo_exchange(c, x, false);
-    spmv_vel<3>(c, x, y, u, poly, pc);
+  if (c->nranks > 1 && c->ph.on && c->vs_valid && c->fused_halo) {
+    size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
+    fused_apply<3>(c, false, fine_dev(c), x, y, u, poly, pc);
+    c->prof.end(id, c->stream);
     return;
   }
-  if (c->ph.on) peer_exchange(c, x, (int)c->S.peer.size(), c->ph.seg_ptr_f, c->ph.src_f, c->ph.land_f, c->ph.total_f_vel, false);
-  else halo_start_velocity(c, x);
-  size_t id = c->prof.begin(PC_SPMV_VEL, c->stream);
-  vel_stream<3, true>(c, fine_dev(c), c->n_tiles_int, c->d_tiles_int.p, x, y, u, poly, pc);
-  if (c->ph.on) peer_wait(c);
-  else CK(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
-  vel_stream<3, true>(c, fine_dev(c), c->n_tiles_bnd, c->d_tiles_bnd.p, x, y, u, poly, pc);
-  c->prof.end(id, c->stream);
+  halo_exchange(c, x, false);
+  spmv_vel<3>(c, x, y, u, poly, pc);
 }
 
 void block_scale(nsb_ctx* c, const double* x, double* y) {
@@ -682,6 +697,12 @@ void level_apply(nsb_ctx* c, PolyLevel& lv, const double* x, double* y, const do
 // one root of a product-form polynomial on a vector whose ghosts are stale
 void level_root(nsb_ctx* c, PolyLevel& lv, double* x, double* y, const double* u, double* poly, PolyCoef pc) {
   if (!lv.coarse) { halo_spmv_vel3(c, x, y, u, poly, pc); return; }
+  if (c->nranks > 1 && c->ph.on && c->fused_halo) {
+    size_t id = c->prof.begin(PC_COARSE, c->stream);
+    fused_apply<3>(c, true, coarse_dev(c), x, y, u, poly, pc);
+    c->prof.end(id, c->stream);
+    return;
+  }
   halo_exchange_coarse(c, x);
   level_apply<3>(c, lv, x, y, u, poly, pc);
 }
@@ -967,8 +988,14 @@ void apply_velocity_pc(nsb_ctx* c, const double* x) {
   c->prof.end(id, c->stream);
   // ---- smoothing from y0:  y = y0 + q(B) (Dinv x - B y0)
   level_block_scale(c, F, x, c->w_u.p);
-  halo_exchange(c, y0, false);
-  level_apply<4>(c, F, y0, F.z0, c->w_u.p, nullptr, PolyCoef{1.0, -1.0, 0.0, 0.0});
+  if (c->nranks > 1 && c->ph.on && c->fused_halo) {
+    size_t idf = c->prof.begin(PC_SPMV_VEL, c->stream);
+    fused_apply<4>(c, false, fine_dev(c), y0, F.z0, c->w_u.p, nullptr, PolyCoef{1.0, -1.0, 0.0, 0.0});
+    c->prof.end(idf, c->stream);
+  } else {
+    halo_exchange(c, y0, false);
+    level_apply<4>(c, F, y0, F.z0, c->w_u.p, nullptr, PolyCoef{1.0, -1.0, 0.0, 0.0});
+  }
   apply_poly(c, F);
   k_axpby<<<nblk(nu, 256), 256, 0, c->stream>>>(nu, 1.0, y0, 1.0, F.poly);
   c->launch_check();
@@ -1235,6 +1262,7 @@ void build_tiles(nsb_ctx* c) {
     c->n_stiles = P.n_tiles();
     c->d_stile_ptr.upload(P.node_ptr, c->stream);
     c->n_tiles_int = (int)P.tiles_int.size(); c->n_tiles_bnd = (int)P.tiles_bnd.size();
+    c->h_tiles_int = P.tiles_int; c->h_tiles_bnd = P.tiles_bnd; c->h_tile_node_ptr = P.node_ptr;
     c->d_tiles_int.upload(P.tiles_int, c->stream); c->d_tiles_bnd.upload(P.tiles_bnd, c->stream);
     c->d_suniq_ptr.upload(P.uniq_ptr, c->stream); c->d_suniq_xoff.upload(P.uniq_xoff, c->stream);
     c->d_spuniq_ptr.upload(P.puniq_ptr, c->stream); c->d_spuniq_xoff.upload(P.puniq_xoff, c->stream);
@@ -1384,6 +1412,39 @@ void setup_peer_halo(nsb_ctx* c, std::vector<DBuf<double>*> fine, std::vector<DB
   H.seg_ptr_f.upload(sp, st); H.src_f.upload(src, st); H.land_f.upload(land, st);
   H.seg_ptr_c.upload(spc, st); H.src_c.upload(srcc, st); H.land_c.upload(landc, st);
   H.d_peer_arena.upload(H.peer_arena, st); H.d_peer_flags.upload(H.peer_flags, st); H.d_peer_rank.upload(pr, st);
+  // fused delivery: per owned node (vertex) the landing offsets in the peers, and the tile lists interior-first
+  auto fused_tables = [&](int n_own, const std::vector<std::vector<int>>& send, const std::vector<long long>& landing, const std::vector<int>& /*t_int*/,
+                          const std::vector<int>& t_bnd, const std::vector<int>& node_ptr, DBuf<int>& d_ptr, DBuf<int2>& d_dst, DBuf<int>& d_list,
+                          int& n_int) {
+    std::vector<int> cnt(n_own + 1, 0);
+    for (int k = 0; k < np; ++k) for (int n : send[k]) cnt[n + 1]++;
+    for (int n = 0; n < n_own; ++n) cnt[n + 1] += cnt[n];
+    std::vector<int2> dst(cnt[n_own]);
+    std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+    for (int k = 0; k < np; ++k)
+      for (size_t i = 0; i < send[k].size(); ++i) dst[fill[send[k][i]]++] = make_int2(k, (int)(landing[k] + (long long)i * dim));
+    // tiles that read ghosts or hold a sent node go to the back of the list: they run after the CTA has seen the peers'
+    // flags, which is also what makes delivering into the peers' buffers safe.  (A sent fine node always has a ghost
+    // neighbour; a sent VERTEX need not have a ghost vertex neighbour -- the peer may only own line nodes next to it.)
+    std::vector<char> back(node_ptr.size() - 1, 0);
+    for (int t : t_bnd) back[t] = 1;
+    for (size_t t = 0; t + 1 < node_ptr.size(); ++t)
+      for (int n = node_ptr[t]; n < node_ptr[t + 1] && !back[t]; ++n)
+        if (cnt[n + 1] != cnt[n]) back[t] = 1;
+    std::vector<int> list;
+    for (size_t t = 0; t + 1 < node_ptr.size(); ++t) if (!back[t]) list.push_back((int)t);
+    n_int = (int)list.size();
+    for (size_t t = 0; t + 1 < node_ptr.size(); ++t) if (back[t]) list.push_back((int)t);
+    for (auto& d : dst) if (d.y < 0) throw CudaErr{"halo plan: negative landing offset"};
+    d_ptr.upload(cnt, st); d_dst.upload(dst, st); d_list.upload(list, st);
+    CK(cudaStreamSynchronize(st));
+  };
+  {
+    std::vector<long long> lf(land.begin(), land.begin() + np);
+    fused_tables(S.nn_own, S.send_nodes, lf, c->h_tiles_int, c->h_tiles_bnd, c->h_tile_node_ptr, H.send_ptr_f, H.send_dst_f, H.list_f, H.n_int_f);
+    fused_tables(S.np_own, S.send_pids, landc, c->cg.h_tiles_int, c->cg.h_tiles_bnd, c->cg.h_tile_node_ptr, H.send_ptr_c, H.send_dst_c, H.list_c, H.n_int_c);
+  }
+  H.fresh_vec = nullptr; H.fresh_seq = 0;
   CK(cudaStreamSynchronize(st));
   nccl_barrier(c);                                   // every rank's flags are zeroed before anybody pushes
   H.on = true;
@@ -1412,6 +1473,7 @@ void build_coarse_level(nsb_ctx* c) {
   const int dim = c->dim;
   G.n_tiles = P.n_tiles();
   G.total_nq = V.total_nq;
+  G.h_tiles_int = P.tiles_int; G.h_tiles_bnd = P.tiles_bnd; G.h_tile_node_ptr = P.node_ptr;
   G.tiles.upload(V.tiles, st); G.meta.upload(V.meta, st); G.uniq_xoff.upload(P.uniq_xoff, st);
   std::vector<long long> t64(Sc.nbr_ptr.begin(), Sc.nbr_ptr.end()), v64(CL.vedge_ptr.begin(), CL.vedge_ptr.end());
   G.nbr_ptr.upload(t64, st); G.vedge_ptr.upload(v64, st);
@@ -1645,6 +1707,8 @@ int nsb_comm_init(nsb_handle c, int rank, int nranks, const void* uid) {
     // (profiles/README.md); meant for larger rank counts, not yet measured there.
     const char* ov = std::getenv("NSB200_OVERLAP");
     c->overlap = ov && ov[0] == '1';
+    const char* fh = std::getenv("NSB200_FUSED_HALO");
+    c->fused_halo = fh && fh[0] == '1';
   }
   c->rank = rank; c->nranks = nranks;
   return 0;
@@ -2272,6 +2336,33 @@ int nsb_test_tile_plan(int dim, int64_t n_vertices, const double* coords, int64_
   return 0;
 }
 
+// host-only: the coarse P1 level of rank `rank` (structure.cpp build_coarse) in GLOBAL ids, for the CPU tests.
+// Two calls: NULL arrays for the sizes.  ends_gid[nn_own][2] = global pressure ids of the end vertices of every owned node,
+// node_gid[nn_own]; vedge pairs (global pressure id of an owned vertex, global node id of a line node ending there);
+// coarse neighbour lists of the owned vertices as (rowptr[np_own+1], global pressure ids), rows = vertex_gid[np_own].
+int nsb_test_coarse_level(int dim, int64_t n_vertices, const double* coords, int64_t n_cells, const uint32_t* cell_vertices,
+                          const uint32_t* cell_dofs, int64_t n_u, int64_t n_p, const int32_t* cell_part, int rank, int nranks,
+                          int64_t* sizes4, int64_t* node_gid, int64_t* ends_gid, int64_t* vedge_pairs, int64_t* vertex_gid,
+                          int64_t* cnbr_ptr, int64_t* cnbr_gid) {
+  Structure S;
+  const std::string e = build_structure(dim, n_vertices, coords, n_cells, cell_vertices, cell_dofs, n_u, n_p,
+                                        nranks > 1 ? cell_part : nullptr, rank, nranks, S);
+  if (!e.empty()) { std::fprintf(stderr, "nsb_test_coarse_level: %s\n", e.c_str()); return -1; }
+  CoarseLevel C;
+  const std::string e2 = build_coarse(S, C);
+  if (!e2.empty()) { std::fprintf(stderr, "nsb_test_coarse_level: %s\n", e2.c_str()); return -1; }
+  sizes4[0] = S.nn_own; sizes4[1] = (int64_t)C.vedge.size(); sizes4[2] = S.np_own; sizes4[3] = (int64_t)C.Sc.nbr.size();
+  if (node_gid) for (int A = 0; A < S.nn_own; ++A) node_gid[A] = S.node_gid[A];
+  if (ends_gid) for (size_t i = 0; i < C.node_ends.size(); ++i) ends_gid[i] = S.pid_gid[C.node_ends[i]];
+  if (vedge_pairs)
+    for (int P = 0; P < S.np_own; ++P)
+      for (int64_t k = C.vedge_ptr[P]; k < C.vedge_ptr[P + 1]; ++k) { vedge_pairs[2 * k] = S.pid_gid[P]; vedge_pairs[2 * k + 1] = S.node_gid[C.vedge[k]]; }
+  if (vertex_gid) for (int P = 0; P < S.np_own; ++P) vertex_gid[P] = S.pid_gid[P];
+  if (cnbr_ptr) std::copy(C.Sc.nbr_ptr.begin(), C.Sc.nbr_ptr.end(), cnbr_ptr);
+  if (cnbr_gid) for (size_t i = 0; i < C.Sc.nbr.size(); ++i) cnbr_gid[i] = S.pid_gid[C.Sc.nbr[i]];
+  return 0;
+}
+
 int nsb_test_hessenberg_eigs(int n, const double* a, double* wr, double* wi) {
   std::vector<double> A(a, a + (size_t)n * n), r, i;
   if (!hessenberg_eigs(n, A, r, i)) return 1;
@@ -2300,6 +2391,18 @@ int nsb_velocity_operator_info(nsb_handle c, int* precision, int64_t* value_byte
   if (index_bytes) *index_bytes = 16 * c->vs_total_nq + 64 * (int64_t)c->n_stiles + 4 * (int64_t)c->d_suniq_xoff.n;
   if (tiles) *tiles = c->n_stiles;
   if (blocks) *blocks = (int64_t)c->S.nbr.size();
+  return 0;
+}
+
+int nsb_comm_info(nsb_handle c, int* nranks, int* halo_mode, int64_t* halo_doubles_per_exchange) {
+  if (!c) return -1;
+  if (nranks) *nranks = c->nranks;
+  if (halo_mode) *halo_mode = c->nranks == 1 ? 0 : !c->ph.on ? 1 : c->fused_halo ? 3 : 2;
+  if (halo_doubles_per_exchange) {
+    int64_t t = 0;
+    for (size_t k = 0; k < c->S.peer.size(); ++k) t += (int64_t)c->S.send_nodes[k].size() * c->dim;
+    *halo_doubles_per_exchange = t;
+  }
   return 0;
 }
 

@@ -90,6 +90,9 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+struct VsHalo;
+template <int DIM> __device__ __forceinline__ void vs_deliver(const VsHalo& hx, int node, int comp, double v);
+
 // the four values of one quad of one plane
 __device__ __forceinline__ void vs_load4(const float* p, double (&v)[4]) {
   const float4 f = *reinterpret_cast<const float4*>(p);
@@ -101,13 +104,37 @@ __device__ __forceinline__ void vs_load4(const __half* p, double (&v)[4]) {
   v[0] = (double)a.x; v[1] = (double)a.y; v[2] = (double)b.x; v[3] = (double)b.y;
 }
 
-// LISTED: the k-th tile of this launch is tile_list[k] (multi-GPU: interior tiles while the halo is in flight, then the
-// boundary tiles).
-template <int DIM, typename VT, int MODE, bool LISTED>
+// Halo exchange FUSED into the operator (several GPUs, peer-store halo of nsb200.cu): the kernel that produces y also
+// delivers it -- the epilogue of a boundary tile stores the rows other ranks hold as ghosts straight into the peers' copies
+// of y over NVLink, and the last consumer warp of the grid to finish raises this rank's sequence flag in every peer -- and
+// the kernel that consumes x waits for the peers' flags itself: tiles are taken from a list with the tiles that read no
+// ghost entry first, and a CTA's producer warp polls the flags only when it reaches its first boundary tile.  A chain of
+// polynomial roots is therefore ONE launch per root, with the exchange hidden behind the interior tiles.
+struct VsHalo {
+  // consuming x
+  const unsigned long long* flags;        // this rank's flag array (sequence numbers written by the peers)
+  const int* peer_rank;
+  int npeers;
+  int n_int;                              // tiles [0, n_int) of the list read no ghost entry
+  unsigned long long wait_seq;            // boundary tiles wait until every peer has reached it (0: ghosts already valid)
+  int ghost_start;                        // offsets >= this are ghost entries of x
+  // delivering y
+  const int* send_ptr;                    // [owned nodes + 1] -> send_dst
+  const int2* send_dst;                   // (peer index, offset of the node's first component inside the peer's vector)
+  double* const* peer_arena;
+  long long y_off;                        // offset of y inside the symmetric arena
+  unsigned long long* const* peer_flags;
+  int my_rank;
+  unsigned long long push_seq;
+  unsigned int* counter;                  // consumer warps of the grid that are done
+};
+
+// HALO: the k-th tile of this launch is tile_list[k], and the exchange of x / y is fused as described above.
+template <int DIM, typename VT, int MODE, bool HALO>
 __global__ void __launch_bounds__(VS_THREADS, 1)
 k_vel_stream(const VsTile* __restrict__ tiles, int n_tiles, const int* __restrict__ tile_list, const VT* __restrict__ vals,
              const uint32_t* __restrict__ meta, const int* __restrict__ uniq_xoff, const double* __restrict__ x,
-             double* __restrict__ y, const double* __restrict__ u, double* __restrict__ poly, PolyCoef pc) {
+             double* __restrict__ y, const double* __restrict__ u, double* __restrict__ poly, PolyCoef pc, VsHalo hx) {
   using L = VsLayout<DIM, VT>;
   constexpr int PL = L::PL;
   constexpr int S = L::STAGES;
@@ -127,12 +154,27 @@ k_vel_stream(const VsTile* __restrict__ tiles, int n_tiles, const int* __restric
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
+    bool waited = false;
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it % S;
       const uint32_t ph = (uint32_t)(it / S) & 1u;
       if (it >= S) mbar_wait(empty + s, ph ^ 1u);                       // consumers released the stage's previous tile
       int t = (int)blockIdx.x + it * (int)gridDim.x;
-      if (LISTED) t = __ldg(tile_list + t);
+      bool ghosts = false;                         // this tile reads ghost entries delivered by peer stores
+      if (HALO) {
+        ghosts = t >= hx.n_int;
+        if (ghosts && !waited) {
+          // first boundary tile of this CTA: the peers' deliveries of x must have landed
+          if (hx.wait_seq && lane < hx.npeers) {
+            const volatile unsigned long long* f = hx.flags + hx.peer_rank[lane];
+            while (*f < hx.wait_seq) { }
+          }
+          __threadfence_system();
+          __syncwarp();
+          waited = true;
+        }
+        t = __ldg(tile_list + t);
+      }
       const VsTile* hd = tiles + t;
       const int NQ = __ldg(&hd->NQ), nq_off = __ldg(&hd->nq_off), u0 = __ldg(&hd->u0), nuq = __ldg(&hd->nuq);
       unsigned char* st = vs_smem + s * L::STAGE_BYTES;
@@ -152,15 +194,43 @@ k_vel_stream(const VsTile* __restrict__ tiles, int n_tiles, const int* __restric
         const int i = lane + 32 * q;
         xo[q] = i < nuq ? __ldg(uniq_xoff + u0 + i) : -1;
       }
+      if (HALO && ghosts) {
+        // ghost entries were written by other GPUs during this kernel: read those through L2 (an L1 line that straddles the
+        // owned / ghost boundary may be stale) and store them; owned entries go the asynchronous way as usual
 #pragma unroll
-      for (int q = 0; q < PER_LANE; ++q) {
-        if (xo[q] >= 0) {
-          const int i = lane + 32 * q;
+        for (int q0 = 0; q0 < PER_LANE; q0 += 4) {
+          double gv[4][DIM];
 #pragma unroll
-          for (int c = 0; c < DIM; ++c) cp_async_8(xs + i * DIM + c, x + xo[q] + c);
+          for (int q = q0; q < q0 + 4; ++q)
+            if (xo[q] >= hx.ghost_start) {
+#pragma unroll
+              for (int c = 0; c < DIM; ++c) gv[q - q0][c] = __ldcg(x + xo[q] + c);
+            }
+#pragma unroll
+          for (int q = q0; q < q0 + 4; ++q) {
+            const int i = lane + 32 * q;
+            if (xo[q] >= hx.ghost_start) {
+#pragma unroll
+              for (int c = 0; c < DIM; ++c) xs[i * DIM + c] = gv[q - q0][c];
+            } else if (xo[q] >= 0) {
+#pragma unroll
+              for (int c = 0; c < DIM; ++c) cp_async_8(xs + i * DIM + c, x + xo[q] + c);
+            }
+          }
         }
+        __threadfence_block();                     // the plain stores above precede the arrival
+        cp_async_arrive_noinc(full + s);
+      } else {
+#pragma unroll
+        for (int q = 0; q < PER_LANE; ++q) {
+          if (xo[q] >= 0) {
+            const int i = lane + 32 * q;
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) cp_async_8(xs + i * DIM + c, x + xo[q] + c);
+          }
+        }
+        cp_async_arrive_noinc(full + s);
       }
-      cp_async_arrive_noinc(full + s);
     }
     return;
   }
@@ -263,20 +333,48 @@ k_vel_stream(const VsTile* __restrict__ tiles, int n_tiles, const int* __restric
     }
     __syncwarp();                                 // this warp's node sums are in ys
     // ---- fused epilogue over this warp's rows (contiguous in memory)
+    const bool deliver = HALO && hx.push_seq && ((int)blockIdx.x + it * (int)gridDim.x) >= hx.n_int;
     for (int i = r0 + lane, q = 0; i < r1; i += 32, ++q) {
       const double t = ys[i];
       if (MODE == 2) {
         y[rowg0 + i] = t;
+        if (deliver) vs_deliver<DIM>(hx, n0 + i / DIM, i % DIM, t);
       } else {
         const double uv = q == 0 ? pu[0] : q == 1 ? pu[1] : u[rowg0 + i];
         const double pv = MODE != 3 ? 0.0 : q == 0 ? pp[0] : q == 1 ? pp[1] : poly[rowg0 + i];
         const double yv = pc.cu * uv + pc.ct * t;
         y[rowg0 + i] = yv;
+        if (deliver) vs_deliver<DIM>(hx, n0 + i / DIM, i % DIM, yv);
         if (MODE == 3) poly[rowg0 + i] = pv + pc.cpu * uv + pc.cpy * yv;
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + s);        // this warp is done with the stage (values, x, sums)
+  }
+  if (HALO && hx.push_seq) {
+    // every consumer warp of the grid checks out once its remote stores are fenced; the last one publishes the sequence
+    // number to the peers
+    __threadfence_system();
+    __syncwarp();
+    unsigned int prev = 0;
+    if (lane == 0) prev = atomicAdd(hx.counter, 1u);
+    prev = __shfl_sync(NSB_FULL, prev, 0);
+    if (prev == gridDim.x * (VS_GROUPS * VS_CONSUMERS) - 1) {
+      __threadfence_system();
+      if (lane < hx.npeers) {
+        volatile unsigned long long* f = hx.peer_flags[lane] + hx.my_rank;
+        *f = hx.push_seq;
+      }
+      if (lane == 0) *hx.counter = 0;
+      __threadfence_system();
+    }
+  }
+}
+
+template <int DIM> __device__ __forceinline__ void vs_deliver(const VsHalo& hx, int node, int comp, double v) {
+  for (int k = __ldg(hx.send_ptr + node); k < __ldg(hx.send_ptr + node + 1); ++k) {
+    const int2 d = __ldg(hx.send_dst + k);
+    hx.peer_arena[d.x][hx.y_off + d.y + comp] = v;
   }
 }
 

@@ -196,3 +196,59 @@ def test_spmv_tile_plan_invariants(golden_mesh, small_3d_mesh, which):
             assert tiles > 0 and n_int + n_bnd == tiles
             assert (n_bnd == 0) if nranks == 1 else (n_bnd > 0)
             assert padded_blocks % 32 == 0 and padded_blocks > 0      # streamed operator: blocks rounded up to 32 per tile
+
+
+@pytest.mark.parametrize("which", ["2d", "3d"])
+def test_coarse_level_is_the_p1_prolongation(golden_mesh, small_3d_mesh, which):
+    """Host structure of the two-level velocity cycle (structure.cpp build_coarse) on 1, 2 and 3 ranks: the end vertices of
+    every owned node give exactly the P1 -> P2 prolongation (vertex nodes weight 1, line nodes 1/2 + 1/2), the line-node lists
+    of the owned vertices are its transpose pattern, and the coarse neighbour lists are the P1 stencil."""
+    import scipy.sparse as sp
+    lib = C.CDLL(LIB, mode=C.RTLD_GLOBAL)
+    m = golden_mesh("mesh-2D") if which == "2d" else small_3d_mesh
+    dim, nv = m.dim, m.dim + 1
+    dm = odofs.enumerate_dofs(m)
+    pts = np.ascontiguousarray(m.points, np.float64)
+    cv = np.ascontiguousarray(m.cells, np.uint32)
+    cd = np.ascontiguousarray(dm.cell_dofs, np.uint32)
+    P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    # reference prolongation on NODES (global node id = velocity dof // dim, global vertex id = pressure dof - n_u)
+    lines = [(0, 1), (1, 2), (2, 0)] if dim == 2 else [(0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3)]
+    cdl = dm.cell_dofs.astype(np.int64)
+    pid = cdl[:, [v * (dim + 1) + dim for v in range(nv)]] - dm.n_u
+    rows, cols, vals = [], [], []
+    for v in range(nv):
+        rows.append(cdl[:, v * (dim + 1)] // dim); cols.append(pid[:, v]); vals.append(np.ones(len(cdl)))
+    for l, (i, j) in enumerate(lines):
+        r = cdl[:, nv * (dim + 1) + dim * l] // dim
+        rows += [r, r]; cols += [pid[:, i], pid[:, j]]; vals += [np.full(len(cdl), 0.5)] * 2
+    rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
+    nn, npv = dm.n_u // dim, dm.n_p
+    _, idx = np.unique(rows * npv + cols, return_index=True)
+    Pref = sp.csr_matrix((vals[idx], (rows[idx], cols[idx])), shape=(nn, npv))
+    p1 = sp.csr_matrix((np.ones(pid.size * nv), (np.repeat(pid, nv, axis=1).ravel(), np.tile(pid, (1, nv)).ravel())), shape=(npv, npv))
+    p1.sum_duplicates(); p1.sort_indices()
+    for nranks in (1, 2, 3):
+        part = (np.arange(m.n_cells, dtype=np.int64) * nranks // m.n_cells).astype(np.int32)
+        seen_nodes, seen_vert = 0, 0
+        for rank in range(nranks):
+            args = (m.dim, C.c_int64(pts.shape[0]), P(pts, C.c_double), C.c_int64(cv.shape[0]), P(cv, C.c_uint32), P(cd, C.c_uint32),
+                    C.c_int64(dm.n_u), C.c_int64(dm.n_p), P(part, C.c_int32) if nranks > 1 else None, rank, nranks)
+            sz = np.zeros(4, np.int64)
+            assert lib.nsb_test_coarse_level(*args, P(sz, C.c_int64), None, None, None, None, None, None) == 0
+            ng, ends, ve = np.empty(sz[0], np.int64), np.empty((sz[0], 2), np.int64), np.empty((sz[1], 2), np.int64)
+            vg, cp, cg = np.empty(sz[2], np.int64), np.empty(sz[2] + 1, np.int64), np.empty(sz[3], np.int64)
+            assert lib.nsb_test_coarse_level(*args, P(sz, C.c_int64), P(ng, C.c_int64), P(ends, C.c_int64), P(ve, C.c_int64), P(vg, C.c_int64),
+                                             P(cp, C.c_int64), P(cg, C.c_int64)) == 0
+            Pl = sp.csr_matrix((np.full(2 * len(ng), 0.5), (np.repeat(ng, 2), ends.ravel())), shape=(nn, npv))
+            Pl.sum_duplicates()
+            sel = sp.csr_matrix((np.ones(len(ng)), (ng, ng)), shape=(nn, nn))
+            assert abs(Pl - sel @ Pref).max() == 0
+            # line nodes at owned vertices = entries of weight 1/2 in the columns of the owned vertices
+            T = Pref.tocsc()[:, vg].tocoo()
+            want = {(int(vg[c_]), int(r_)) for r_, c_, w_ in zip(T.row, T.col, T.data) if w_ == 0.5}
+            assert want == {(int(a_), int(b_)) for a_, b_ in ve}
+            for k, v_ in enumerate(vg):
+                assert np.array_equal(np.sort(cg[cp[k]:cp[k + 1]]), p1.indices[p1.indptr[v_]:p1.indptr[v_ + 1]])
+            seen_nodes += len(ng); seen_vert += len(vg)
+        assert seen_nodes == nn and seen_vert == npv

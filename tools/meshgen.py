@@ -233,6 +233,16 @@ def _locality_order_2d(p, t):
     return p[order], remap[t], remap
 
 
+def cached_cross_section(level):
+    """Cross-section triangulation cached by tools/make_cross_sections.py (identical to what cross_section() returns)."""
+    import os
+    f = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cross_sections", "level%d.npz" % level)
+    if not os.path.exists(f):
+        return None
+    d = np.load(f)
+    return d["p2"], d["t2"], d["be2"], d["tag2"]
+
+
 def mesh_3d(level=None, lc_cyl=None, lc_global=None, nx=None, verbose=False, cross=None) -> Mesh:
     """mesh-3D-<level>-equivalent (level in {5,10,20,40}) or explicit sizes."""
     if level is not None:
@@ -240,6 +250,8 @@ def mesh_3d(level=None, lc_cyl=None, lc_global=None, nx=None, verbose=False, cro
     if nx is None:
         nx = int(np.ceil(W3 / lc_cyl))
         nx += nx % 2                                   # a node layer at x = W/2 = 0.205
+    if cross is None and level is not None:
+        cross = cached_cross_section(level)
     p2, t2, be2, tag2 = cross if cross is not None else cross_section(lc_cyl, lc_global, verbose=verbose)
     p2, t2, remap = _locality_order_2d(p2, t2)
     be2 = remap[be2]
