@@ -329,6 +329,7 @@ struct nsb_ctx {
   PeerHalo ph;
   PolyLevel lvF, lvC;
   bool two_level = false;           // the last setup chose the two-level cycle
+  bool cycle_disabled = false;      // the cycle stalled on this mesh / flow regime: single-level polynomial from now on (reset by a new mesh or new options)
   DBuf<double> V;                   // Krylov basis, (m+1) vectors of n_own
   int V_cap = 0;
   DBuf<double> partial, d_h, d_nrm;
@@ -837,7 +838,7 @@ void level_arnoldi(nsb_ctx* c, PolyLevel& lv, int dmax, double target) {
   lv.ritz_top = std::max(lv.ritz_top, lv.ritz_hi);
 }
 
-bool level_spectrum_is_real(const PolyLevel& lv) { return lv.ritz_lo > 0 && lv.ritz_im < 0.05 * lv.ritz_hi; }
+bool level_spectrum_is_real(const PolyLevel& lv, double tol = 0.05) { return lv.ritz_lo > 0 && lv.ritz_im < tol * lv.ritz_hi; }
 
 // roots of the degree-d Chebyshev polynomial on [lo, hi], Leja ordered
 void set_roots(PolyLevel& lv, std::vector<double> wr, std::vector<double> wi) {
@@ -929,11 +930,12 @@ template <int DIM> void launch_coarse_assemble(nsb_ctx* c) {
 // Rebuilds the velocity preconditioner for the currently assembled system (once per solve, or every poly_refresh-th).
 void setup_velocity_pc(nsb_ctx* c) {
   PolyLevel& F = c->lvF;
-  bool two = c->opt.velocity_cycle != 1 && c->cg.valid && c->vs_valid;
+  bool two = c->opt.velocity_cycle != 1 && c->cg.valid && c->vs_valid && !c->cycle_disabled;
   if (two) {
-    // fine level: only the upper end of the spectrum of B is needed for the smoother
-    level_arnoldi(c, F, 12, 0.0);
-    two = level_spectrum_is_real(F);
+    // fine level: the upper end of the spectrum of B for the smoother, and enough Arnoldi steps to see whether the
+    // spectrum leaves the real axis (convection-dominated 2-D flows: the Chebyshev smoother would amplify those modes)
+    level_arnoldi(c, F, 24, 0.0);
+    two = level_spectrum_is_real(F, 0.02);
   }
   c->two_level = two;
   if (!two) {
@@ -1825,7 +1827,7 @@ int nsb_upload_mesh(nsb_handle c, int64_t n_vertices, const double* coords, int6
   CK(cudaStreamSynchronize(st));
   c->have_mesh = true; c->have_matrix = false; c->have_pressure = false;
   bind_fine_level(c);
-  c->lvF.probe_init = false; c->lvF.roots.clear(); c->solves = 0; c->V_cap = 0; c->two_level = false;
+  c->lvF.probe_init = false; c->lvF.roots.clear(); c->solves = 0; c->V_cap = 0; c->two_level = false; c->cycle_disabled = false;
   c->halo.clear();                 // pack lists of the previous mesh
   return 0;
   NSB_CATCH(c)
@@ -1936,6 +1938,7 @@ int nsb_set_solver_opts(nsb_handle c, const nsb_solver_opts* o) {
   if (!(n.smoother_hi_factor >= 1.0)) n.smoother_hi_factor = 1.1;
   const bool changed = n.precond_precision != c->opt.precond_precision;
   c->opt = n;
+  c->cycle_disabled = false;
   if (c->have_mesh && changed) {
     // (de)allocate the packed operator copy of the velocity polynomial; it is refilled by the next assembly
     try {
@@ -2121,7 +2124,20 @@ int nsb_solve(nsb_handle c, int max_it, double tol_rel, int n_tmp, int* iteratio
   double res = 0;
   if (c->lvF.roots.empty() || c->solves % c->opt.poly_refresh == 0) setup_velocity_pc(c);
   const double bnorm = device_norm2(c, c->v_rhs.p, c->S.n_own_dofs());
-  const int rc = gmres(c, max_it, tol_rel * bnorm, n_tmp > 2 ? n_tmp : 150, &it, &res);
+  int rc = gmres(c, max_it, tol_rel * bnorm, n_tmp > 2 ? n_tmp : 150, &it, &res);
+  if (c->two_level && (rc == 1 || it > 100)) {
+    // The two-level cycle is only a good preconditioner while the scaled velocity spectrum stays near the real axis; when
+    // it stalls (developing convection in the 2-D cases) the robust single-level polynomial takes over for the rest of the
+    // run -- and a solve the cycle failed on is repeated with it before non-convergence is reported to the caller, so
+    // that the reference's fallback branches (cpp:1241-1286) only fire for reasons the reference would have too.
+    c->cycle_disabled = true;
+    if (rc == 1) {
+      setup_velocity_pc(c);
+      int it2 = 0;
+      rc = gmres(c, max_it, tol_rel * bnorm, n_tmp > 2 ? n_tmp : 150, &it2, &res);
+      it = it2;
+    }
+  }
   // constraints.distribute(x)   (cpp:566, 862)
   if (c->n_con) {
     k_scatter_vals<<<nblk(c->n_con, 256), 256, 0, c->stream>>>(c->n_con, c->c_idx.p, c->c_val.p, c->v_sol.p);
