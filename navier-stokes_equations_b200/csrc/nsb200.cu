@@ -310,14 +310,8 @@ struct nsb_ctx {
   double Mp_lmax = 1.0;
   std::vector<std::unique_ptr<DevLevel>> amg;
   std::vector<std::unique_ptr<HaloBuf>> halo;
-  // halo / compute overlap of the velocity polynomial (multi-GPU): tiles that read no ghost entry run while the
-  // exchange is in flight on comm_stream, the boundary tiles after it
-  cudaStream_t comm_stream = nullptr;
-  cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;
-  DBuf<int> d_tiles_int, d_tiles_bnd;
-  int n_tiles_int = 0, n_tiles_bnd = 0;
+  int n_tiles_int = 0, n_tiles_bnd = 0;   // SpMV tiles without / with ghost reads
   std::vector<int> h_tiles_int, h_tiles_bnd, h_tile_node_ptr;     // host copies (fused halo tables)
-  bool overlap = false;
   bool fused_halo = false;          // halo exchange fused into the streamed operator (peer-store halo only): NSB200_FUSED_HALO=1.
                                     // Off by default: measured 4-5 % slower than the separate push / wait kernels on 2 GPUs (profiles/README.md)
   double* pin = nullptr;           // pinned staging buffer for host <-> device vector traffic (n_tot doubles)
@@ -1265,7 +1259,6 @@ void build_tiles(nsb_ctx* c) {
     c->d_stile_ptr.upload(P.node_ptr, c->stream);
     c->n_tiles_int = (int)P.tiles_int.size(); c->n_tiles_bnd = (int)P.tiles_bnd.size();
     c->h_tiles_int = P.tiles_int; c->h_tiles_bnd = P.tiles_bnd; c->h_tile_node_ptr = P.node_ptr;
-    c->d_tiles_int.upload(P.tiles_int, c->stream); c->d_tiles_bnd.upload(P.tiles_bnd, c->stream);
     c->d_suniq_ptr.upload(P.uniq_ptr, c->stream); c->d_suniq_xoff.upload(P.uniq_xoff, c->stream);
     c->d_spuniq_ptr.upload(P.puniq_ptr, c->stream); c->d_spuniq_xoff.upload(P.puniq_xoff, c->stream);
     c->d_nbr_loc.upload(P.nbr_loc, c->stream); c->d_pnbr_loc.upload(P.pnbr_loc, c->stream);
@@ -1665,9 +1658,6 @@ int nsb_destroy(nsb_handle c) {
     // peers may still map this rank's arena: close our mappings, then rendezvous before anything is freed
     try { close_peer_halo(c); nccl_barrier(c); } catch (...) {}
   }
-  if (c->comm_stream) { cudaStreamSynchronize(c->comm_stream); cudaStreamDestroy(c->comm_stream); }
-  if (c->ev_pack) cudaEventDestroy(c->ev_pack);
-  if (c->ev_halo) cudaEventDestroy(c->ev_halo);
   if (c->pin) cudaFreeHost(c->pin);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   if (c->t0) cudaEventDestroy(c->t0);
@@ -1701,14 +1691,7 @@ int nsb_comm_init(nsb_handle c, int rank, int nranks, const void* uid) {
     ncclUniqueId id;
     std::memcpy(&id, uid, sizeof(id));
     CKN(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
-    CK(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
-    // NSB200_OVERLAP=1 enables the halo / compute overlap of the velocity polynomial.  Off by default: on 2 GPUs
-    // with 0.2 ms local SpMVs the split into two launches costs more than the 35 us exchange it hides
-    // (profiles/README.md); meant for larger rank counts, not yet measured there.
-    const char* ov = std::getenv("NSB200_OVERLAP");
-    c->overlap = ov && ov[0] == '1';
+    // NSB200_FUSED_HALO=1: halo exchange fused into the streamed velocity operator (peer-store halo only)
     const char* fh = std::getenv("NSB200_FUSED_HALO");
     c->fused_halo = fh && fh[0] == '1';
   }

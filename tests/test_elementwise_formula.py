@@ -1,8 +1,8 @@
-"""CPU checks of the algebra behind the element-wise velocity operator (csrc/ebe.cuh), against the oracle's cell
-matrices: (1) every velocity-velocity cell block of the linearised system is delta_cd S_ab + gamma G^{cd}_ab with
-G = |J| g^T Khat g, for every u* regime and with SUPG; (2) the closed-form grad-div action used by the kernel
-(div x_h is P1 on the cell) equals G x.  The GPU test test_elementwise_velocity_operator_equals_assembled checks
-the kernel itself."""
+"""CPU checks, against the oracle's cell matrices, of the algebra the assembly and the two-level velocity cycle rest on
+(csrc/assemble.cuh, csrc/twolevel.cuh): (1) every velocity-velocity cell block of the linearised system is
+delta_cd S_ab + gamma G^{cd}_ab with G = |J| g^T Khat g, for every u* regime and with SUPG; (2) the closed-form grad-div
+action (div x_h is P1 on the cell) equals G x.  The GPU tests test_linearized_assembly_parity and
+test_coarse_operator_is_the_galerkin_product check the kernels themselves."""
 import math
 
 import numpy as np

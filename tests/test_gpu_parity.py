@@ -151,6 +151,20 @@ def test_pressure_matrices_spmv_and_solve(case2d, case3d, which):
     assert it3 == it2 and np.array_equal(xs, c.dev.get_vector(nsb.NSB_SOLUTION))
 
 
+def test_zero_initialised_solver_opts_mean_the_defaults(nsb):
+    """A zero-initialised nsb_solver_opts (what RunOptions::solver{} and the C facade pass) selects the library defaults
+    for every field, including the Gram-Schmidt policy (0 used to switch the second pass off)."""
+    dev = nsb.Device(2)
+    base = dev.get_solver_opts()
+    dev.set_solver_opts()                     # all fields zero
+    got = dev.get_solver_opts()
+    assert got == base and got["reorthogonalize"] == 1 and got["velocity_cycle"] == 2 and got["precond_precision"] in (16, 32)
+    dev.set_solver_opts(reorthogonalize=-1, precond_precision=64, velocity_cycle=1)
+    got = dev.get_solver_opts()
+    assert got["reorthogonalize"] == -1 and got["precond_precision"] == 64 and got["velocity_cycle"] == 1
+    dev.close()
+
+
 def test_error_paths(nsb, golden_mesh):
     m = golden_mesh("mesh-2D")
     dm = odofs.enumerate_dofs(m)
