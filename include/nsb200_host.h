@@ -30,6 +30,7 @@ typedef struct nsh_options {
   int32_t max_steps;         /* run(): stop after this many steps; <0 = until T                  */
   const char* output_dir;    /* NULL = "./"                                                      */
   nsb_solver_opts solver;    /* zero = defaults                                                  */
+  int32_t partitioner;       /* cells -> ranks: 0 contiguous chunks (default), 1 METIS on the face-dual graph (cpp:56) */
   int32_t test_fail_solves;  /* test hook: report the next k linear solves as not converged (drives the retry /
                                 fallback paths of run(), cpp:1174-1198, 1223-1286); 0 in production           */
 } nsh_options;
@@ -61,6 +62,8 @@ int nshd_get_sizes(nshd_handle h, int64_t* n_u, int64_t* n_p, int64_t* n_cells, 
 int nshd_get_mesh(nshd_handle h, double* points, uint32_t* cells);
 int nshd_get_cell_dofs(nshd_handle h, uint32_t* cell_dofs);
 int nshd_get_support_points(nshd_handle h, double* pts, unsigned char* component);
+/* owning rank of every cell for `nranks` ranks: method 0 contiguous chunks, 1 METIS (GridTools::partition_triangulation, cpp:56) */
+int nshd_partition(nshd_handle h, int nranks, int method, int32_t* cell_part);
 /* make_sparsity_pattern(dh, bdsp, empty_constraints, true): call with NULLs to get nnz first */
 int nshd_get_pattern(nshd_handle h, int64_t* nnz, int64_t* rowptr, uint32_t* col);
 /* Dirichlet lines in the reference's order inlet -> walls -> cylinder (velocity), outlet (pressure).

@@ -296,7 +296,7 @@ _hostlib = None
 class NshOptions(C.Structure):
     _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("nccl_unique_id", C.c_void_p),
                 ("write_vtu", C.c_int32), ("verbose", C.c_int32), ("gmres_tolerance", C.c_double), ("deltat", C.c_double),
-                ("max_steps", C.c_int32), ("output_dir", C.c_char_p), ("solver", NsbSolverOpts), ("test_fail_solves", C.c_int32)]
+                ("max_steps", C.c_int32), ("output_dir", C.c_char_p), ("solver", NsbSolverOpts), ("partitioner", C.c_int32), ("test_fail_solves", C.c_int32)]
 
 
 class NshStepInfo(C.Structure):
@@ -332,12 +332,12 @@ class HostSolver:
     """NavierStokes<dim>(TestCases::make_<case>(mesh_file)) driven through the C facade."""
 
     def __init__(self, case, mesh_file, device=0, rank=0, nranks=1, nccl_unique_id=None, write_vtu=False, verbose=False,
-                 gmres_tolerance=0.0, deltat=0.0, output_dir=None, solver_opts=None, test_fail_solves=0):
+                 gmres_tolerance=0.0, deltat=0.0, output_dir=None, solver_opts=None, test_fail_solves=0, partitioner=0):
         L = hostlib()
         self._uid = C.create_string_buffer(nccl_unique_id, 128) if nccl_unique_id else None
         self._outdir = output_dir.encode() if output_dir else None
         o = NshOptions(device, rank, nranks, C.cast(self._uid, C.c_void_p) if self._uid else None, int(write_vtu),
-                       int(verbose), gmres_tolerance, deltat, -1, self._outdir, solver_opts or NsbSolverOpts(), test_fail_solves)
+                       int(verbose), gmres_tolerance, deltat, -1, self._outdir, solver_opts or NsbSolverOpts(), partitioner, test_fail_solves)
         self.h = C.c_void_p()
         if L.nsh_create(case.encode(), mesh_file.encode(), C.byref(o), C.byref(self.h)) != 0:
             raise NsbError(L.nsh_last_error().decode())
@@ -425,6 +425,13 @@ class HostSetup:
         v = np.empty(n.value)
         hostlib().nshd_get_constraints(self.h, case.encode(), C.c_double(t), int(homogeneous), C.byref(n), _p(d, C.c_uint32), _p(v, C.c_double))
         return d, v
+
+    def partition(self, nranks, method=0):
+        """Owning rank of every cell: method 0 contiguous chunks, 1 METIS on the face-dual graph."""
+        part = np.empty(self.n_cells, np.int32)
+        if hostlib().nshd_partition(self.h, int(nranks), int(method), _p(part, C.c_int32)) != 0:
+            raise NsbError(hostlib().nsh_last_error().decode())
+        return part
 
     def mesh(self):
         p = np.empty((self.n_vertices, self.dim))

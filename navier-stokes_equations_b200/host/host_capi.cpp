@@ -68,6 +68,7 @@ int nsh_create(const char* test_case, const char* mesh_file, const nsh_options* 
     ro.max_steps = o->max_steps;
     if (o->output_dir) ro.output_dir = o->output_dir;
     ro.solver = o->solver;
+    ro.partitioner = o->partitioner;
     ro.test_fail_solves = o->test_fail_solves;
     dt = o->deltat;
   }
@@ -176,6 +177,14 @@ int nshd_get_support_points(nshd_handle h, double* pts, unsigned char* comp) {
   if (pts) std::memcpy(pts, h->dh.support_points.data(), h->dh.support_points.size() * sizeof(double));
   if (comp) std::memcpy(comp, h->dh.component.data(), h->dh.component.size());
   return 0;
+}
+
+int nshd_partition(nshd_handle h, int nranks, int method, int32_t* cell_part) {
+  NSH_TRY
+  const std::vector<int32_t> p = partition_cells(h->mesh, nranks, method);
+  std::copy(p.begin(), p.end(), cell_part);
+  return 0;
+  NSH_CATCH
 }
 
 int nshd_get_pattern(nshd_handle h, int64_t* nnz, int64_t* rowptr, uint32_t* col) {

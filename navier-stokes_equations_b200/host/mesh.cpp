@@ -128,6 +128,57 @@ FaceKey make_key(int dim, const uint32_t* fv) {
 }
 }  // namespace
 
+extern "C" {
+// METIS 5 API of the toolkit's static library (no header shipped): idx_t = int64_t, real_t = float
+int METIS_SetDefaultOptions(int64_t* options);
+int METIS_PartGraphRecursive(int64_t* nvtxs, int64_t* ncon, int64_t* xadj, int64_t* adjncy, int64_t* vwgt, int64_t* vsize, int64_t* adjwgt,
+                             int64_t* nparts, float* tpwgts, float* ubvec, int64_t* options, int64_t* objval, int64_t* part);
+int METIS_PartGraphKway(int64_t* nvtxs, int64_t* ncon, int64_t* xadj, int64_t* adjncy, int64_t* vwgt, int64_t* vsize, int64_t* adjwgt,
+                        int64_t* nparts, float* tpwgts, float* ubvec, int64_t* options, int64_t* objval, int64_t* part);
+}
+
+std::vector<int32_t> partition_cells(const Mesh& m, int nparts, int method) {
+  const int64_t C = m.n_cells();
+  std::vector<int32_t> part((size_t)C, 0);
+  if (nparts <= 1) return part;
+  if (method == 0) {
+    for (int64_t c = 0; c < C; ++c) part[c] = (int32_t)((c * (int64_t)nparts) / C);
+    return part;
+  }
+  // face-dual graph: two cells are adjacent when they share a face
+  const int dim = m.dim, NV = dim + 1;
+  std::vector<std::pair<FaceKey, int64_t>> all;
+  all.reserve((size_t)C * NV);
+  for (int64_t c = 0; c < C; ++c)
+    for (int f = 0; f < NV; ++f) {
+      uint32_t fv[3] = {0, 0, 0};
+      const int* lv = face_vertices(dim, f);
+      for (int i = 0; i < dim; ++i) fv[i] = m.cells[(size_t)c * NV + lv[i]];
+      all.push_back({make_key(dim, fv), c});
+    }
+  std::sort(all.begin(), all.end());
+  std::vector<int64_t> deg((size_t)C + 1, 0);
+  for (size_t i = 0; i + 1 < all.size(); ++i)
+    if (!(all[i].first < all[i + 1].first) && !(all[i + 1].first < all[i].first)) { deg[all[i].second + 1]++; deg[all[i + 1].second + 1]++; }
+  for (int64_t c = 0; c < C; ++c) deg[c + 1] += deg[c];
+  std::vector<int64_t> adj((size_t)deg[C]), fill(deg.begin(), deg.end() - 1);
+  for (size_t i = 0; i + 1 < all.size(); ++i)
+    if (!(all[i].first < all[i + 1].first) && !(all[i + 1].first < all[i].first)) {
+      adj[fill[all[i].second]++] = all[i + 1].second;
+      adj[fill[all[i + 1].second]++] = all[i].second;
+    }
+  for (int64_t c = 0; c < C; ++c) std::sort(adj.begin() + deg[c], adj.begin() + deg[c + 1]);
+  int64_t nv = C, ncon = 1, np = nparts, objval = 0;
+  int64_t options[64];
+  METIS_SetDefaultOptions(options);
+  std::vector<int64_t> p64((size_t)C, 0);
+  const int rc = (nparts <= 8 ? METIS_PartGraphRecursive : METIS_PartGraphKway)(&nv, &ncon, deg.data(), adj.data(), nullptr, nullptr, nullptr, &np,
+                                                                                nullptr, nullptr, options, &objval, p64.data());
+  if (rc != 1) throw std::runtime_error("METIS partitioning failed");
+  for (int64_t c = 0; c < C; ++c) part[c] = (int32_t)p64[c];
+  return part;
+}
+
 std::vector<BoundaryFace> boundary_faces(const Mesh& m) {
   const int dim = m.dim, NV = dim + 1;
   // count face occurrences

@@ -35,6 +35,13 @@ std::vector<BoundaryFace> boundary_faces(const Mesh& m);
 bool assign_boundary_ids_geometrically(const Mesh& m, std::vector<BoundaryFace>& bf, int inlet, int outlet, int wall,
                                        int cylinder);
 
+// Cell partition for `nparts` ranks (reference cpp:56: GridTools::partition_triangulation = METIS on the face-neighbour graph
+// of the cells, PartGraphRecursive for <= 8 parts, Kway beyond, default options).
+//   method 0: contiguous chunks of the cell order (default: deterministic, no third-party code on the path)
+//   method 1: METIS on the face-dual graph through the header-less libmetis_static.a of the CUDA toolkit (idx_t = int64);
+//             layouts then depend on that METIS build, like the reference's depend on its own
+std::vector<int32_t> partition_cells(const Mesh& m, int nparts, int method);
+
 // local face -> local vertices, deal.II ReferenceCells::Triangle / Tetrahedron
 inline const int* face_vertices(int dim, int f) {
   static const int tri[3][3] = {{0, 1, -1}, {1, 2, -1}, {2, 0, -1}};

@@ -124,12 +124,11 @@ template <int dim> void NavierStokes<dim>::setup() {
   // contiguous chunks (the reference: METIS through GridTools::partition_triangulation, cpp:56).
   ck(nsb_create(dim, options.device, &dev), "nsb_create");
   if (!dev) throw std::runtime_error("nsb_create failed (no usable CUDA device)");
-  std::vector<int32_t> part;
+  std::vector<int32_t>& part = cell_part;
+  part.clear();
   if (mpi_size > 1) {
     ck(nsb_comm_init(dev, (int)mpi_rank, (int)mpi_size, options.nccl_unique_id), "nsb_comm_init");
-    const int64_t C = mesh.n_cells();
-    part.resize(C);
-    for (int64_t c = 0; c < C; ++c) part[c] = (int32_t)((c * (int64_t)mpi_size) / C);   // output() lists the same chunks
+    part = partition_cells(mesh, (int)mpi_size, options.partitioner);     // cpp:56; output() writes the same ownership
   }
   ck(nsb_set_solver_opts(dev, &options.solver), "nsb_set_solver_opts");
   ck(nsb_upload_mesh(dev, mesh.n_vertices(), mesh.points.data(), mesh.n_cells(), mesh.cells.data(),
@@ -409,13 +408,15 @@ template <int dim> void NavierStokes<dim>::output(const unsigned int time_step) 
   if (!options.write_vtu) return;
   // One piece per rank holding that rank's OWNED cells (DataOut::write_vtu_with_pvtu_record, cpp:1037-1041):
   // solution_NNNN.<rank>.vtu with velocity (vector), pressure and subdomain, and solution_NNNN.pvtu on rank 0
-  // listing every piece.  Ownership = the contiguous cell chunks handed to nsb_upload_mesh in setup().
+  // listing every piece.  Ownership = the cell partition handed to nsb_upload_mesh in setup().
   const int NV = dim + 1;
   const int64_t C = mesh.n_cells();
-  const int64_t c0 = (C * (int64_t)mpi_rank + mpi_size - 1) / mpi_size, c1 = (C * (int64_t)(mpi_rank + 1) + mpi_size - 1) / mpi_size;
+  std::vector<int64_t> owned;
+  for (int64_t c = 0; c < C; ++c)
+    if (cell_part.empty() || cell_part[c] == (int32_t)mpi_rank) owned.push_back(c);
   // vertices used by the owned cells, renumbered in order of first use
   std::vector<int64_t> vmap((size_t)mesh.n_vertices(), -1), vlist;
-  for (int64_t c = c0; c < c1; ++c)
+  for (int64_t c : owned)
     for (int k = 0; k < NV; ++k) {
       const uint32_t v = mesh.cells[(size_t)c * NV + k];
       if (vmap[v] < 0) { vmap[v] = (int64_t)vlist.size(); vlist.push_back(v); }
@@ -423,7 +424,7 @@ template <int dim> void NavierStokes<dim>::output(const unsigned int time_step) 
   char name[256];
   std::snprintf(name, sizeof(name), "%ssolution_%04u.%u.vtu", options.output_dir.c_str(), time_step, mpi_rank);
   std::ofstream f(name);
-  const int64_t V = (int64_t)vlist.size(), CL = c1 - c0;
+  const int64_t V = (int64_t)vlist.size(), CL = (int64_t)owned.size();
   f << std::setprecision(9);
   f << "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<UnstructuredGrid>\n";
   f << "<Piece NumberOfPoints=\"" << V << "\" NumberOfCells=\"" << CL << "\">\n<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n";
@@ -432,7 +433,7 @@ template <int dim> void NavierStokes<dim>::output(const unsigned int time_step) 
     f << "\n";
   }
   f << "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int64\" Name=\"connectivity\" format=\"ascii\">\n";
-  for (int64_t c = c0; c < c1; ++c) {
+  for (int64_t c : owned) {
     for (int k = 0; k < NV; ++k) f << vmap[mesh.cells[(size_t)c * NV + k]] << " ";
     f << "\n";
   }

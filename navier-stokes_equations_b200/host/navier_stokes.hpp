@@ -78,6 +78,7 @@ struct RunOptions {
   int max_steps = -1;             // stop run() after this many time steps (-1: until T)
   std::string output_dir = "./";
   nsb_solver_opts solver{};       // zero = library defaults
+  int partitioner = 0;            // cells -> ranks: 0 = contiguous chunks, 1 = METIS on the face-dual graph (partition_cells, mesh.hpp)
   int test_fail_solves = 0;       // test hook: the next k linear solves are REPORTED as not converged (their result is kept,
                                   // as the reference keeps the iterate of a failed GMRES) -> drives run()'s retry / fallback paths
 };
@@ -185,6 +186,7 @@ protected:
   bool first_step = true, second_step = true;
   bool pressure_matrices_assembled = false;
   Constraints newton_constraints, system_constraints;
+  std::vector<int32_t> cell_part;       // owning rank of every cell (several ranks)
   std::ofstream forces_file;
   unsigned int time_step_no = 0;
   int last_gmres_iterations = 0, step_gmres_iterations = 0, step_solves = 0;

@@ -252,3 +252,64 @@ def test_coarse_level_is_the_p1_prolongation(golden_mesh, small_3d_mesh, which):
                 assert np.array_equal(np.sort(cg[cp[k]:cp[k + 1]]), p1.indices[p1.indptr[v_]:p1.indptr[v_ + 1]])
             seen_nodes += len(ng); seen_vert += len(vg)
         assert seen_nodes == nn and seen_vert == npv
+
+
+@pytest.mark.parametrize("which", ["2d", "3d"])
+def test_metis_partition_and_structure_on_it(golden_mesh, small_3d_mesh, msh_file, tmp_path, which):
+    """partition_cells(method 1) = METIS on the face-dual graph (GridTools::partition_triangulation, reference cpp:56): every
+    cell gets a rank, parts are balanced, the face cut beats contiguous chunks of an unordered cell list -- and the device
+    structure builder, the SpMV tile plans and the streamed-operator plans hold their invariants on such a (non-contiguous)
+    partition: rows partitioned exactly, every row keeps its global pattern, ghosts = sends."""
+    from tools import msh as mshmod
+    import nsb200 as nsb
+    lib = C.CDLL(LIB, mode=C.RTLD_GLOBAL)
+    if which == "2d":
+        m, path = golden_mesh("mesh-2D"), msh_file("mesh-2D")
+    else:
+        m, path = small_3d_mesh, str(tmp_path / "m3.bin")
+        mshmod.write_bin(path, m)
+    hs = nsb.HostSetup(path, m.dim)
+    dm = odofs.enumerate_dofs(m)
+    orp, ocol = odofs.make_sparsity(dm)
+    nv = m.dim + 1
+    # faces shared by two cells
+    faces = {}
+    lv = [[0, 1], [1, 2], [2, 0]] if m.dim == 2 else [[0, 1, 2], [1, 0, 3], [0, 2, 3], [2, 1, 3]]
+    for f in lv:
+        for c, key in enumerate(map(tuple, np.sort(m.cells[:, f], axis=1))):
+            faces.setdefault(key, []).append(c)
+    pairs = np.array([v for v in faces.values() if len(v) == 2])
+
+    def cut(part):
+        return int(np.count_nonzero(part[pairs[:, 0]] != part[pairs[:, 1]]))
+
+    pts = np.ascontiguousarray(m.points, np.float64)
+    cv = np.ascontiguousarray(m.cells, np.uint32)
+    cd = np.ascontiguousarray(dm.cell_dofs, np.uint32)
+    P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    for R in (2, 3, 8):
+        chunks, metis = hs.partition(R, 0), hs.partition(R, 1)
+        assert np.array_equal(chunks, (np.arange(m.n_cells, dtype=np.int64) * R // m.n_cells).astype(np.int32))
+        assert metis.min() == 0 and metis.max() == R - 1
+        sizes = np.bincount(metis, minlength=R)
+        assert sizes.max() <= 1.06 * m.n_cells / R + 1, sizes
+        assert cut(metis) < cut(np.random.default_rng(0).permutation(chunks))
+        if R == 8:
+            continue
+        seen = np.zeros(dm.n_dofs, int)
+        ghosts = sends = 0
+        for r in range(R):
+            rp, col, gid, ng, ns, nc = _build_pattern(lib, m.dim, m, dm, metis, r, R)
+            seen[gid] += 1
+            assert np.array_equal(np.diff(rp), np.diff(orp)[gid])
+            for k in range(0, gid.size, max(1, gid.size // 200)):
+                g = gid[k]
+                assert np.array_equal(col[rp[k]:rp[k + 1]].astype(np.int64), ocol[orp[g]:orp[g + 1]].astype(np.int64))
+            ghosts += ng; sends += ns
+            out = np.zeros(5, np.int64)
+            assert lib.nsb_test_tile_plan(m.dim, C.c_int64(pts.shape[0]), P(pts, C.c_double), C.c_int64(cv.shape[0]), P(cv, C.c_uint32),
+                                          P(cd, C.c_uint32), C.c_int64(dm.n_u), C.c_int64(dm.n_p), P(np.ascontiguousarray(metis, np.int32), C.c_int32),
+                                          r, R, P(out, C.c_int64)) == 0
+            assert out[4] == 0 and out[2] > 0, out
+        assert np.all(seen == 1) and ghosts == sends > 0
+    hs.close()

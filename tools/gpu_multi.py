@@ -29,6 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default=None)
     ap.add_argument("--lc", type=float, default=0.04)
+    ap.add_argument("--part", default="chunks", help="cell partition: chunks (contiguous) or metis (face-dual graph, like the reference)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -69,6 +70,12 @@ def main():
     dev = nsb.Device(3, local)
     dev.comm_init(rank, world, holder[0])
     part = (np.arange(mesh.n_cells, dtype=np.int64) * world // mesh.n_cells).astype(np.int32)
+    if args.part == "metis":
+        tmpm = tempfile.mkdtemp(prefix="nsb_part_%d_" % rank)
+        msh.write_bin(tmpm + "/m.bin", mesh)
+        hsu = nsb.HostSetup(tmpm + "/m.bin", 3)
+        part = hsu.partition(world, 1)
+        hsu.close()
     setup(dev, part)
     nrows, nnz, nc = dev.sizes()
     rp, col = dev.pattern()
@@ -96,7 +103,7 @@ def main():
     rec = dict(rank=rank, world=world, rows=int(nrows), cells=int(nc), pattern_ok=bool(okpat), A_relerr=float(errA),
                A_bitexact_vs_1gpu=bool(bitexact), b_relerr=float(errb), b_bitexact_vs_1gpu=b_bitexact,
                gmres_ok=bool(ok), gmres_its=int(it), gmres_its_1gpu=int(it1), tight_ok=bool(ok2), tight_its=int(it2),
-               field_relerr_vs_direct=ferr, fused=os.environ.get("NSB200_FUSED_HALO", "1"), halo=os.environ.get("NSB200_HALO", "p2p"))
+               field_relerr_vs_direct=ferr, fused=os.environ.get("NSB200_FUSED_HALO", "0"), halo=os.environ.get("NSB200_HALO", "p2p"))
     print("[rank %d/%d] " % (rank, world) + json.dumps(rec), flush=True)
     dist.barrier()
     dev.close()
@@ -110,7 +117,7 @@ def main():
     holder3 = [nsb.Device.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(holder3, src=0)
     hs = nsb.HostSolver("3D-2Z", path, device=local, rank=rank, nranks=world, nccl_unique_id=holder3[0], gmres_tolerance=1e-12,
-                        write_vtu=True, output_dir=outdir)
+                        write_vtu=True, output_dir=outdir, partitioner=1 if args.part == "metis" else 0)
     hs.initialize()
     infos = [hs.step() for _ in range(3)]
     steps = []
@@ -135,7 +142,7 @@ def main():
         for src in pieces:
             piece = ET.parse(outdir + src).getroot().find("UnstructuredGrid/Piece")
             ncell += int(piece.get("NumberOfCells"))
-        summary = dict(world=world, fused=os.environ.get("NSB200_FUSED_HALO", "1"), halo=os.environ.get("NSB200_HALO", "p2p"), mesh_cells=int(mesh.n_cells), n_dofs=int(N),
+        summary = dict(world=world, partition=args.part, fused=os.environ.get("NSB200_FUSED_HALO", "0"), halo=os.environ.get("NSB200_HALO", "p2p"), mesh_cells=int(mesh.n_cells), n_dofs=int(N),
                        ranks=recs, host_class_steps=steps, host_class_field_relerr=field, vtu_pieces=pieces, vtu_cells_total=ncell)
         print("[summary] " + json.dumps(summary), flush=True)
         if args.json:
