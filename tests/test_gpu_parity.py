@@ -225,11 +225,21 @@ def test_host_class_3d_steps_match_oracle(nsb, small_3d_mesh, tmp_path):
             assert abs(info[key] - ref[key]) <= TOL_FORCE * abs(ref[key]) + 1e-12, (k, key, info[key], ref[key])
         x = s.solution()
         assert np.linalg.norm(x - o.current_solution) / np.linalg.norm(o.current_solution) < TOL_FIELD
-    # reference stopping rule (1e-2): same trajectory to the accuracy that tolerance allows
+    # reference stopping rule (1e-2 * ||b|| on the preconditioned residual): converged, within the 200-iteration cap, and the
+    # same first step as the tight-tolerance trajectory to the accuracy that stopping rule leaves (measured on a B200: C_D
+    # 2e-7, dp 1e-8 relative after 17 iterations; the bound is loose on purpose -- two preconditioners stopped at 1e-2 may
+    # differ by up to that tolerance)
     s2 = nsb.HostSolver("3D-2Z", path)
     s2.initialize()
     info = s2.step()
-    assert info["converged"] == 1 and info["gmres_iterations"] > 0
+    o1 = osolve.Oracle(small_3d_mesh, "3D-2Z", solver="direct")
+    ref1 = o1.step()
+    assert info["converged"] == 1 and 0 < info["gmres_iterations"] <= 200 and info["solves"] == 1
+    loose = {key: abs(info[key] - ref1[key]) / max(abs(ref1[key]), 1e-300) for key in ("cd", "dp")}
+    print("first step at the reference tolerance vs direct solve:", loose, "GMRES", info["gmres_iterations"])
+    assert loose["cd"] < 5e-2 and loose["dp"] < 5e-2, loose
+    x2 = s2.solution()
+    assert np.linalg.norm(x2 - o1.current_solution) / np.linalg.norm(o1.current_solution) < 5e-2
     s.close()
     s2.close()
 
