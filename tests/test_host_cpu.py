@@ -313,3 +313,55 @@ def test_metis_partition_and_structure_on_it(golden_mesh, small_3d_mesh, msh_fil
             assert out[4] == 0 and out[2] > 0, out
         assert np.all(seen == 1) and ghosts == sends > 0
     hs.close()
+
+
+@pytest.mark.parametrize("which", ["2d", "3d"])
+def test_coarse_level_references_are_covered_by_the_vertex_halo(golden_mesh, small_3d_mesh, which):
+    """Several ranks: every coarse vertex a rank's two-level cycle touches -- the end vertices of its owned nodes
+    (prolongation) and the P1 neighbours of its owned vertices (coarse operator) -- is an owned vertex or one of the
+    pressure ghosts the halo plan delivers (the coarse vectors travel with the pressure-halo plan, dim components per
+    vertex), for contiguous chunks and for a METIS partition."""
+    import nsb200 as nsb
+    from tools import msh as mshmod
+    import tempfile
+    lib = C.CDLL(LIB, mode=C.RTLD_GLOBAL)
+    m = golden_mesh("mesh-2D") if which == "2d" else small_3d_mesh
+    dm = odofs.enumerate_dofs(m)
+    pts = np.ascontiguousarray(m.points, np.float64)
+    cv = np.ascontiguousarray(m.cells, np.uint32)
+    cd = np.ascontiguousarray(dm.cell_dofs, np.uint32)
+    P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "m.bin")
+        mshmod.write_bin(path, m)
+        hs = nsb.HostSetup(path, m.dim)
+        parts = {("chunks", R): hs.partition(R, 0) for R in (2, 3)}
+        parts[("metis", 3)] = hs.partition(3, 1)
+        hs.close()
+    for (kind, R), part in parts.items():
+        part = np.ascontiguousarray(part, np.int32)
+        for rank in range(R):
+            args = (m.dim, C.c_int64(pts.shape[0]), P(pts, C.c_double), C.c_int64(cv.shape[0]), P(cv, C.c_uint32), P(cd, C.c_uint32),
+                    C.c_int64(dm.n_u), C.c_int64(dm.n_p), P(part, C.c_int32), rank, R)
+            sz = np.zeros(4, np.int64)
+            assert lib.nsb_test_coarse_level(*args, P(sz, C.c_int64), None, None, None, None, None, None) == 0
+            ng, ends, ve = np.empty(sz[0], np.int64), np.empty((sz[0], 2), np.int64), np.empty((sz[1], 2), np.int64)
+            vg, cp, cg = np.empty(sz[2], np.int64), np.empty(sz[2] + 1, np.int64), np.empty(sz[3], np.int64)
+            assert lib.nsb_test_coarse_level(*args, P(sz, C.c_int64), P(ng, C.c_int64), P(ends, C.c_int64), P(ve, C.c_int64), P(vg, C.c_int64),
+                                             P(cp, C.c_int64), P(cg, C.c_int64)) == 0
+            nghost, npeers = C.c_int64(), C.c_int32()
+            assert lib.nsb_test_halo_plan(*args, C.byref(nghost), None, C.byref(npeers), None, None, None, None, None, None, None) == 0
+            ghost = np.empty(nghost.value, np.int64)
+            K = npeers.value
+            peers = np.empty(K, np.int32)
+            su_ptr, sp_ptr, ru, rpc = np.empty(K + 1, np.int64), np.empty(K + 1, np.int64), np.empty(K, np.int64), np.empty(K, np.int64)
+            assert lib.nsb_test_halo_plan(*args, C.byref(nghost), P(ghost, C.c_int64), C.byref(npeers), P(peers, C.c_int32), P(su_ptr, C.c_int64), None,
+                                          P(sp_ptr, C.c_int64), None, P(ru, C.c_int64), P(rpc, C.c_int64)) == 0
+            ghost_vertices = ghost[ghost >= dm.n_u] - dm.n_u              # pressure ghosts = ghost vertices
+            assert ghost_vertices.size == int(rpc.sum())
+            have = set(vg.tolist()) | set(ghost_vertices.tolist())
+            need = set(ends.ravel().tolist()) | set(cg.tolist())
+            assert need <= have, (kind, R, rank, len(need - have))
+            # line nodes listed at owned vertices are local nodes (owned or velocity ghosts)
+            ghost_nodes = np.unique(ghost[ghost < dm.n_u] // m.dim)
+            assert set(ve[:, 1].tolist()) <= set(ng.tolist()) | set(ghost_nodes.tolist())
